@@ -1,0 +1,634 @@
+// Persistent grouped tcgen05 GEMM with fused epilogues (see gemm.cuh for the role on the hot path).
+//
+// CTA = 192 threads, one CTA per SM (smem-limited):
+//   warp 0   : tile scheduler + TMA producer (one elected lane)
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane)
+//   warps 2-5: epilogue; warp w owns TMEM lanes / tile rows 32*(w%4) .. +31
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator ring full/empty (MMA <-> epilogue,
+// 2 x 256 columns so the next tile's MMAs overlap this tile's epilogue), tile-id ring (scheduler ->
+// MMA/epilogue; tiles are claimed with an atomic counter so long wgrad tiles and short dgrad tiles of
+// one launch balance across the 148 SMs).
+#include "gemm.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+#include "philox.cuh"
+#include "ptx.cuh"
+
+namespace tfk {
+
+namespace {
+
+constexpr uint32_t A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t B_TILE_BYTES = BN * BK * 2;  // 32 KB
+constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr uint32_t SLAB_BYTES = 32 * 128;  // 32 rows x 128 B, one epilogue warp's staging buffer
+constexpr uint32_t SLABS_OFF = STAGES * STAGE_BYTES;
+constexpr uint32_t BARS_OFF = SLABS_OFF + 4 * 2 * SLAB_BYTES;
+constexpr int SCHED_DEPTH = 4;
+constexpr uint32_t SMEM_USED = BARS_OFF + 256;
+constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-byte alignment
+constexpr uint32_t MN_ATOM_BYTES = 64 * BK * 2;    // one 64(MN) x 64(K) TMA box = 8 KB
+
+struct SmemBars {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t sched_full[SCHED_DEPTH];
+  uint64_t sched_empty[SCHED_DEPTH];
+  int tile_ring[SCHED_DEPTH];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemBars) <= 256, "barrier block too large");
+
+struct TileCoord {
+  int p, m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
+  TileCoord t;
+  t.p = (P.nprob > 1 && tile >= P.p[1].tile_begin) ? 1 : 0;
+  const int local = tile - P.p[t.p].tile_begin;
+  const int tn = P.p[t.p].tiles_n;
+  t.m_blk = local / tn;
+  t.n_blk = local - t.m_blk * tn;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Sum v[0..31] over the 32 lanes; lane L returns the total of column L (31 shuffles, not 160).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float keep = up ? v[j + s] : v[j];
+      const float send = up ? v[j] : v[j + s];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue for one 128 x 256 accumulator tile, executed by the four epilogue warps.
+// ------------------------------------------------------------------------------------------------
+template <int OUT>
+__device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tmem_acc, int m0,
+                                              int n0, uint32_t q, uint32_t lane, uint32_t slab_base,
+                                              int& sbuf) {
+  const int row = m0 + static_cast<int>(q * 32 + lane);
+  const bool row_ok = row < pr.M;
+  const uint32_t lane_taddr = tmem_acc + ((q * 32u) << 16);
+  const uint32_t row_off = lane * 128u;
+  const uint32_t sw = lane & 7u;
+
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    // bf16 outputs are emitted in 64-column groups (two chunks), fp32 outputs per 32-column chunk
+    const int group_col0 = (OUT == OUT_BF16 || OUT == OUT_BF16_SPLIT) ? (n0 + (c & ~1) * 32) : col0;
+    if (group_col0 >= pr.N) break;  // warp-uniform
+
+    uint32_t r[32];
+    tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(c * 32), r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+
+    if (pr.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
+      const float4* bp = reinterpret_cast<const float4*>(pr.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(bp + j);
+        v[4 * j + 0] += b.x;
+        v[4 * j + 1] += b.y;
+        v[4 * j + 2] += b.z;
+        v[4 * j + 3] += b.w;
+      }
+    }
+    if (pr.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
+      float s1[32], s2[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float z = row_ok ? v[j] : 0.f;
+        s1[j] = z;
+        s2[j] = z * z;
+      }
+      const float t1 = warp_transpose_reduce(s1, lane);
+      const float t2 = warp_transpose_reduce(s2, lane);
+      const int col = col0 + static_cast<int>(lane);
+      if (col < pr.N) {
+        const size_t o = static_cast<size_t>((m0 >> 5) + q) * pr.stat_ld + col;
+        pr.stat_sum[o] = t1;
+        pr.stat_sq[o] = t2;
+      }
+    }
+    if (pr.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (pr.drop_thr != 0u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const Philox4 rnd =
+            philox4x32_10(static_cast<uint32_t>(col0 >> 2) + j, static_cast<uint32_t>(row), 0u, 0u,
+                          static_cast<uint32_t>(pr.seed), static_cast<uint32_t>(pr.seed >> 32));
+        v[4 * j + 0] = ((rnd.x >> 8) >= pr.drop_thr) ? v[4 * j + 0] * pr.keep_inv : 0.f;
+        v[4 * j + 1] = ((rnd.y >> 8) >= pr.drop_thr) ? v[4 * j + 1] * pr.keep_inv : 0.f;
+        v[4 * j + 2] = ((rnd.z >> 8) >= pr.drop_thr) ? v[4 * j + 2] * pr.keep_inv : 0.f;
+        v[4 * j + 3] = ((rnd.w >> 8) >= pr.drop_thr) ? v[4 * j + 3] * pr.keep_inv : 0.f;
+      }
+    }
+    if (pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
+      const __nv_bfloat16* mp = pr.mask_src + static_cast<size_t>(row) * pr.mask_ld + col0;
+      if (row_ok && col0 + 32 <= pr.N) {
+        const uint4* mp4 = reinterpret_cast<const uint4*>(mp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 m = __ldg(mp4 + j);
+          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+            const bool plo = (lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0;
+            const bool phi = (hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0;
+            v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * pr.scale : 0.f;
+            v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * pr.scale : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = row_ok && (col0 + j) < pr.N;
+          const float mv = ok ? __bfloat162float(mp[j]) : 0.f;
+          v[j] = (mv > 0.f) ? v[j] * pr.scale : 0.f;
+        }
+      }
+    }
+
+    if constexpr (OUT == OUT_F32 || OUT == OUT_F32_REDADD) {
+      if (lane == 0) tma_wait_group_read<1>();  // the slab written two stores ago is free again
+      __syncwarp();
+      const uint32_t slab = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES + row_off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t addr = slab + ((static_cast<uint32_t>(j) ^ sw) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
+                     "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t src = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES;
+        if constexpr (OUT == OUT_F32)
+          tma_store_2d(&pr.tmD[0], src, col0, m0 + static_cast<int>(q * 32));
+        else
+          tma_reduce_add_2d(&pr.tmD[0], src, col0, m0 + static_cast<int>(q * 32));
+        tma_commit_group();
+      }
+      sbuf ^= 1;
+    } else if constexpr (OUT == OUT_BF16) {
+      const int half = c & 1;
+      if (half == 0) {
+        if (lane == 0) tma_wait_group_read<1>();
+        __syncwarp();
+      }
+      const uint32_t slab = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES + row_off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t addr = slab + ((static_cast<uint32_t>(half * 4 + j) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                     "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])),
+                     "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                     "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                     "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                     : "memory");
+      }
+      if (half == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&pr.tmD[0], slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES, group_col0,
+                       m0 + static_cast<int>(q * 32));
+          tma_commit_group();
+        }
+        sbuf ^= 1;
+      }
+    } else {  // OUT_BF16_SPLIT: slab 0 = hi, slab 1 = lo
+      const int half = c & 1;
+      if (half == 0) {
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
+      }
+      const uint32_t slab_hi = slab_base + row_off;
+      const uint32_t slab_lo = slab_base + SLAB_BYTES + row_off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = v[8 * j + 2 * k], b = v[8 * j + 2 * k + 1];
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+          const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+          __nv_bfloat162 h2;
+          h2.x = ah;
+          h2.y = bh;
+          hi[k] = *reinterpret_cast<uint32_t*>(&h2);
+          lo[k] = pack_bf16x2(ar, br);
+        }
+        const uint32_t off = ((static_cast<uint32_t>(half * 4 + j) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_hi + off), "r"(hi[0]),
+                     "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_lo + off), "r"(lo[0]),
+                     "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
+                     : "memory");
+      }
+      if (half == 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&pr.tmD[0], slab_base, group_col0, m0 + static_cast<int>(q * 32));
+          tma_store_2d(&pr.tmD[1], slab_base + SLAB_BYTES, group_col0,
+                       m0 + static_cast<int>(q * 32));
+          tma_commit_group();
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  SmemBars* bars = reinterpret_cast<SmemBars*>(smem_gen + BARS_OFF);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.nprob; ++p) {
+      tma_prefetch_desc(&P.p[p].tmA[0]);
+      tma_prefetch_desc(&P.p[p].tmB[0]);
+      tma_prefetch_desc(&P.p[p].tmD[0]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&bars->full[i], 1);
+        mbar_init(&bars->empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->tmem_full[i], 1);
+        mbar_init(&bars->tmem_empty[i], 4);
+      }
+      for (int i = 0; i < SCHED_DEPTH; ++i) {
+        mbar_init(&bars->sched_full[i], 1);
+        mbar_init(&bars->sched_empty[i], 5);  // MMA thread + 4 epilogue warps
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ============================ scheduler + TMA producer ============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int tile = blockIdx.x;
+      for (int it = 0;; ++it) {
+        const int slot = it % SCHED_DEPTH;
+        mbar_wait(&bars->sched_empty[slot], (((it / SCHED_DEPTH) & 1) ^ 1));
+        bars->tile_ring[slot] = tile;
+        mbar_arrive(&bars->sched_full[slot]);
+        if (tile >= P.total_tiles) break;
+
+        const TileCoord tc = decode_tile(P, tile);
+        const GemmProblem& pr = P.p[tc.p];
+        const int m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
+        const int iters = pr.num_kb * pr.nsplit;
+        int kb = 0, s = 0;
+        for (int i = 0; i < iters; ++i) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+          // bf16x3: s=0 -> (A_hi,B_hi), s=1 -> (A_hi,B_lo), s=2 -> (A_lo,B_hi)
+          const CUtensorMap* ta = &pr.tmA[s == 2 ? 1 : 0];
+          const CUtensorMap* tb = &pr.tmB[s == 1 ? 1 : 0];
+          const int k0 = kb * BK;
+          if (pr.a_mn) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * MN_ATOM_BYTES, ta, &bars->full[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sa, ta, &bars->full[stage], k0, m0);
+          }
+          if (pr.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * MN_ATOM_BYTES, tb, &bars->full[stage], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sb, tb, &bars->full[stage], k0, n0);
+          }
+          if (++s == pr.nsplit) {
+            s = 0;
+            ++kb;
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tile = atomicAdd(&P.sched[0], 1) + static_cast<int>(gridDim.x);
+      }
+      // self-resetting scheduler counters: the last CTA to finish claiming tiles zeroes them
+      __threadfence();
+      const int done = atomicAdd(&P.sched[1], 1);
+      if (done == static_cast<int>(gridDim.x) - 1) {
+        P.sched[0] = 0;
+        P.sched[1] = 0;
+        __threadfence();
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0;; ++it) {
+        const int slot = it % SCHED_DEPTH;
+        mbar_wait(&bars->sched_full[slot], (it / SCHED_DEPTH) & 1);
+        const int tile = bars->tile_ring[slot];
+        mbar_arrive(&bars->sched_empty[slot]);
+        if (tile >= P.total_tiles) break;
+
+        const TileCoord tc = decode_tile(P, tile);
+        const GemmProblem& pr = P.p[tc.p];
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        const uint32_t idesc = make_idesc_bf16(BM, BN, pr.a_mn, pr.b_mn);
+        // K-major: 8-row x 128B atoms, SBO = 1024 B, advance 32 B per UMMA_K inside the swizzled row.
+        // MN-major: 64(MN) x 8(K) atoms, SBO = 1024 B between K groups, LBO = 8 KB between MN atoms,
+        //           advance 2 K-groups (2048 B) per UMMA_K.
+        const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
+        const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
+        const int iters = pr.num_kb * pr.nsplit;
+        for (int i = 0; i < iters; ++i) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
+            const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
+            umma_bf16(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&bars->tmem_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ============================ epilogue warps ============================
+    const uint32_t q = warp & 3;
+    const uint32_t slab_base = smem_base + SLABS_OFF + (warp - 2) * 2 * SLAB_BYTES;
+    int sbuf = 0, prev_split = 0;
+    for (int it = 0;; ++it) {
+      const int slot = it % SCHED_DEPTH;
+      mbar_wait(&bars->sched_full[slot], (it / SCHED_DEPTH) & 1);
+      const int tile = bars->tile_ring[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->sched_empty[slot]);
+      if (tile >= P.total_tiles) break;
+
+      const TileCoord tc = decode_tile(P, tile);
+      const GemmProblem& pr = P.p[tc.p];
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN;
+      const int m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
+      // A split store reads BOTH slabs of this warp: drain before switching store discipline.
+      const int is_split = pr.out_kind == OUT_BF16_SPLIT;
+      if (is_split != prev_split) {
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
+        prev_split = is_split;
+        sbuf = 0;
+      }
+      switch (pr.out_kind) {
+        case OUT_BF16:
+          epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+          break;
+        case OUT_BF16_SPLIT:
+          epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+          break;
+        case OUT_F32:
+          epilogue_tile<OUT_F32>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+          break;
+        default:
+          epilogue_tile<OUT_F32_REDADD>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+          break;
+      }
+      // all tcgen05.ld of this accumulator are complete (tmem_ld_wait) -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+    }
+    if (lane == 0) tma_wait_group<0>();  // smem must outlive the bulk stores; make them complete
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  // resolved at run time so the library has no link-time dependency on libcuda.so
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* ptr,
+              uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
+              uint32_t box_outer, char* err, int errlen) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -2;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * elem_bytes) % 16 != 0) {
+    snprintf(err, errlen, "TMA operand %p pitch %llu B is not 16-byte aligned", ptr,
+             (unsigned long long)(pitch_elems * elem_bytes));
+    return -1;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu pitch=%llu", (int)r,
+             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems);
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t gemm_smem_bytes() { return SMEM_BYTES; }
+
+int gemm_init() {
+  static int done = 0;
+  if (done) return 0;
+  cudaError_t e = cudaFuncSetAttribute(tfk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  done = 1;
+  return 0;
+}
+
+int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* out, char* err,
+                      int errlen) {
+  if (nspec < 1 || nspec > 2) {
+    snprintf(err, errlen, "gemm_build_params: nspec must be 1 or 2");
+    return -1;
+  }
+  memset(out, 0, sizeof(GemmParams));
+  out->nprob = nspec;
+  out->sched = sched;
+  int tile_begin = 0;
+  for (int i = 0; i < nspec; ++i) {
+    const GemmSpec& s = specs[i];
+    GemmProblem& p = out->p[i];
+    if (s.M <= 0 || s.N <= 0 || s.K <= 0) {
+      snprintf(err, errlen, "gemm: empty problem M=%d N=%d K=%d", s.M, s.N, s.K);
+      return -1;
+    }
+    if (s.nsplit != 1 && s.nsplit != 3) {
+      snprintf(err, errlen, "gemm: nsplit must be 1 or 3");
+      return -1;
+    }
+    int rc;
+    for (int h = 0; h < (s.nsplit == 3 ? 2 : 1); ++h) {
+      const __nv_bfloat16* a = h ? s.A_lo : s.A_hi;
+      const __nv_bfloat16* b = h ? s.B_lo : s.B_hi;
+      if (!a || !b) {
+        snprintf(err, errlen, "gemm: missing operand pointer");
+        return -1;
+      }
+      if (s.a_mn)
+        rc = make_tmap(&p.tmA[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, s.M, s.K, s.lda, 64, BK, err,
+                       errlen);
+      else
+        rc = make_tmap(&p.tmA[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, s.K, s.M, s.lda, BK, BM, err,
+                       errlen);
+      if (rc) return rc;
+      if (s.b_mn)
+        rc = make_tmap(&p.tmB[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, s.N, s.K, s.ldb, 64, BK, err,
+                       errlen);
+      else
+        rc = make_tmap(&p.tmB[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, s.K, s.N, s.ldb, BK, BN, err,
+                       errlen);
+      if (rc) return rc;
+    }
+    if (s.out_kind == OUT_F32 || s.out_kind == OUT_F32_REDADD) {
+      rc = make_tmap(&p.tmD[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s.D_hi, s.N, s.M, s.ldd, 32, 32,
+                     err, errlen);
+      if (rc) return rc;
+    } else {
+      rc = make_tmap(&p.tmD[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s.D_hi, s.N, s.M, s.ldd, 64, 32,
+                     err, errlen);
+      if (rc) return rc;
+      if (s.out_kind == OUT_BF16_SPLIT) {
+        rc = make_tmap(&p.tmD[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s.D_lo, s.N, s.M, s.ldd, 64, 32,
+                       err, errlen);
+        if (rc) return rc;
+      }
+    }
+    p.M = s.M;
+    p.N = s.N;
+    p.K = s.K;
+    p.a_mn = s.a_mn;
+    p.b_mn = s.b_mn;
+    p.nsplit = s.nsplit;
+    p.out_kind = s.out_kind;
+    p.relu = s.relu;
+    p.mask_ld = s.mask_ld;
+    p.scale = s.scale;
+    p.keep_inv = 1.0f / s.keep;
+    p.drop_thr = (s.keep < 1.0f) ? dropout_threshold(s.keep) : 0u;
+    p.bias = s.bias;
+    p.mask_src = s.mask_src;
+    p.seed = s.seed;
+    p.stat_sum = s.stat_sum;
+    p.stat_sq = s.stat_sq;
+    p.stat_ld = s.stat_ld;
+    p.tiles_m = (s.M + BM - 1) / BM;
+    p.tiles_n = (s.N + BN - 1) / BN;
+    p.tile_begin = tile_begin;
+    p.num_kb = (s.K + BK - 1) / BK;
+    tile_begin += p.tiles_m * p.tiles_n;
+  }
+  out->total_tiles = tile_begin;
+  return 0;
+}
+
+int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream) {
+  int rc = gemm_init();
+  if (rc) return rc;
+  const int grid = params.total_tiles < num_sms ? params.total_tiles : num_sms;
+  tfk_gemm_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(params);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tfk

@@ -1,0 +1,99 @@
+// Persistent grouped GEMM for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by
+// TMA into 128B-swizzled shared memory, fused epilogue, TMA store / TMA reduce-add.
+//
+// One launch runs up to two "problems" D = A.B^T (UMMA convention: A is [M,K], B is [N,K], both may
+// be K-major or MN-major in memory).  The three uses on the tfkaldi hot path
+// (reference: neuralNetworks/classifiers/layer.py:52  `tf.matmul(inputs, weights) + biases`,
+//  and its tf.gradients twin, neuralNetworks/trainer.py:155):
+//   forward  Y[B,N]   = X[B,K] . W[K,N]      A = X  (K-major)   B = W  (MN-major)
+//   dgrad    dX[B,K]  = dZ[B,N] . W[K,N]^T   A = dZ (K-major)   B = W  (K-major, W row = output col)
+//   wgrad    dW[K,N] += X[B,K]^T . dZ[B,N]   A = X  (MN-major)  B = dZ (MN-major), TMA reduce-add
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tfk {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int TMEM_COLS = 512;     // 2 accumulator stages x 256 fp32 columns
+
+enum OutKind : int {
+  OUT_BF16 = 0,        // D_hi = bf16(v)
+  OUT_BF16_SPLIT = 1,  // D_hi = bf16(v), D_lo = bf16(v - D_hi)   (fp32-equivalent storage)
+  OUT_F32 = 2,         // D_hi(f32) = v
+  OUT_F32_REDADD = 3,  // D_hi(f32) += v   (TMA reduce-add; split-K and micro-batch accumulation)
+};
+
+// Host-side description of one GEMM.  All matrices are row-major with a leading dimension in
+// elements; bf16 leading dimensions must be multiples of 8, fp32 ones multiples of 4 (16-byte TMA pitch).
+struct GemmSpec {
+  int M = 0, N = 0, K = 0;
+  const __nv_bfloat16* A_hi = nullptr;
+  const __nv_bfloat16* A_lo = nullptr;
+  int lda = 0;
+  int a_mn = 0;  // 0: A stored [M,K];  1: A stored [K,M]
+  const __nv_bfloat16* B_hi = nullptr;
+  const __nv_bfloat16* B_lo = nullptr;
+  int ldb = 0;
+  int b_mn = 0;    // 0: B stored [N,K];  1: B stored [K,N]
+  int nsplit = 1;  // 1: plain bf16;  3: bf16x3 (Ah.Bh + Ah.Bl + Al.Bh), ~fp32 accuracy
+  int out_kind = OUT_BF16;
+  void* D_hi = nullptr;
+  void* D_lo = nullptr;
+  int ldd = 0;
+  const float* bias = nullptr;  // [>= roundup(N,256)] added per column, or null
+  int relu = 0;
+  const __nv_bfloat16* mask_src = nullptr;  // [M, mask_ld]: v = mask_src>0 ? v*scale : 0
+  int mask_ld = 0;
+  float scale = 1.0f;
+  // forward dropout (reference: classifiers/activation.py:140-141): keep<1 => v = v/keep * floor(keep+u)
+  float keep = 1.0f;
+  unsigned long long seed = 0;  // Philox key; counter = row*N + col
+  // per-(128-row tile, column) partial sums of v and v*v taken BEFORE relu/dropout (batch-norm stats)
+  float* stat_sum = nullptr;  // [tiles_m, stat_ld]
+  float* stat_sq = nullptr;
+  int stat_ld = 0;
+};
+
+struct alignas(64) GemmProblem {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  CUtensorMap tmD[2];
+  int M, N, K;
+  int a_mn, b_mn, nsplit, out_kind;
+  int relu, mask_ld;
+  float scale, keep_inv;
+  unsigned int drop_thr;  // keep element iff (philox >> 8) >= drop_thr; 0 => no dropout
+  const float* bias;
+  const __nv_bfloat16* mask_src;
+  unsigned long long seed;
+  float* stat_sum;
+  float* stat_sq;
+  int stat_ld;
+  int tiles_m, tiles_n, tile_begin, num_kb;
+};
+
+struct alignas(64) GemmParams {
+  GemmProblem p[2];
+  int nprob;
+  int total_tiles;
+  int* sched;  // [2]: {next tile counter, finished-CTA counter}; self-resetting
+};
+
+// Build the kernel parameters (tensor maps) for up to two problems.  Long-K problems should come first.
+// Returns 0 on success, negative on error (message in err).
+int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* out, char* err,
+                      int errlen);
+// Launch on `stream`.  `num_sms` = multiprocessor count of the current device.
+int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream);
+// One-time (per process) kernel attribute setup; returns cudaError_t as int.
+int gemm_init();
+size_t gemm_smem_bytes();
+
+}  // namespace tfk

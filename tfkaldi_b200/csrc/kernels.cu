@@ -1,0 +1,651 @@
+// HBM-bound kernels of the hot path: coalesced, 128-bit vectorised accesses, one pass where possible.
+#include "kernels.cuh"
+
+#include <cfloat>
+
+#include "philox.cuh"
+
+namespace tfk {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  __nv_bfloat162 h;
+  h.x = ah;
+  h.y = bh;
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = pack2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void split_f32_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int ld_dst, int rows, int cols,
+                                 int vec_ok) {
+  const int groups = ld_dst >> 2;
+  const size_t total = static_cast<size_t>(rows) * groups;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / groups);
+    const int c = static_cast<int>(i - static_cast<size_t>(r) * groups) << 2;
+    float x[4];
+    const float* sp = src + static_cast<size_t>(r) * ld_src + c;
+    if (vec_ok && c + 4 <= cols) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(sp));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = (c + k < cols) ? __ldg(sp + k) : 0.f;
+    }
+    uint2 h, l;
+    split2(x[0], x[1], h.x, l.x);
+    split2(x[2], x[3], h.y, l.y);
+    const size_t o = static_cast<size_t>(r) * ld_dst + c;
+    *reinterpret_cast<uint2*>(hi + o) = h;
+    if (lo) *reinterpret_cast<uint2*>(lo + o) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp per row; the row lives in registers (NV float4 per lane) so logits are read once.
+template <int NV>
+__global__ void __launch_bounds__(256)
+softmax_ce_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels, int B,
+                  int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
+                  __nv_bfloat16* __restrict__ d_lo) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int nvec = ld >> 2;
+  const float4* zp = reinterpret_cast<const float4*>(logits + static_cast<size_t>(row) * ld);
+  float4 z[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (idx < nvec) {
+      t = __ldg(zp + idx);
+      const int e = idx << 2;
+      if (e + 1 > O) t.x = -INFINITY;
+      if (e + 2 > O) t.y = -INFINITY;
+      if (e + 3 > O) t.z = -INFINITY;
+      if (e + 4 > O) t.w = -INFINITY;
+    }
+    z[i] = t;
+    mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+  }
+  mx = warp_max(mx);
+  const int label = labels[row];
+  const bool label_ok = label >= 0 && label < O;
+  float sum = 0.f, zl = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) << 2;
+    if (label_ok && (label >> 2) == (lane + 32 * i)) {
+      const int t = label & 3;
+      zl = t == 0 ? z[i].x : t == 1 ? z[i].y : t == 2 ? z[i].z : z[i].w;
+    }
+    z[i].x = expf(z[i].x - mx);
+    z[i].y = expf(z[i].y - mx);
+    z[i].z = expf(z[i].z - mx);
+    z[i].w = expf(z[i].w - mx);
+    sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
+    (void)e;
+  }
+  sum = warp_sum(sum);
+  zl = warp_sum(zl);
+  if (lane == 0) row_loss[row] = label_ok ? (logf(sum) + mx - zl) : 0.f;
+  if (d_hi == nullptr) return;
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx >= nvec) continue;
+    const int e = idx << 2;
+    float p[4] = {z[i].x * inv, z[i].y * inv, z[i].z * inv, z[i].w * inv};
+    if (!label_ok) p[0] = p[1] = p[2] = p[3] = 0.f;
+    else if ((label >> 2) == idx) p[label & 3] -= 1.0f;
+    uint2 h, l;
+    split2(p[0], p[1], h.x, l.x);
+    split2(p[2], p[3], h.y, l.y);
+    const size_t o = static_cast<size_t>(row) * ld + e;
+    *reinterpret_cast<uint2*>(d_hi + o) = h;
+    if (d_lo) *reinterpret_cast<uint2*>(d_lo + o) = l;
+  }
+}
+
+// Any O: three passes over the row (the re-reads hit L1/L2).
+__global__ void __launch_bounds__(256)
+softmax_ce_generic_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels,
+                          int B, int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
+                          __nv_bfloat16* __restrict__ d_lo) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* zp = logits + static_cast<size_t>(row) * ld;
+  float mx = -INFINITY;
+  for (int e = lane; e < O; e += 32) mx = fmaxf(mx, zp[e]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int e = lane; e < O; e += 32) sum += expf(zp[e] - mx);
+  sum = warp_sum(sum);
+  const int label = labels[row];
+  const bool label_ok = label >= 0 && label < O;
+  if (lane == 0) row_loss[row] = label_ok ? (logf(sum) + mx - zp[label]) : 0.f;
+  if (d_hi == nullptr) return;
+  const float inv = 1.0f / sum;
+  for (int e = lane; e < ld; e += 32) {
+    float p = (e < O && label_ok) ? expf(zp[e] - mx) * inv : 0.f;
+    if (label_ok && e == label) p -= 1.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(p);
+    d_hi[static_cast<size_t>(row) * ld + e] = h;
+    if (d_lo) d_lo[static_cast<size_t>(row) * ld + e] = __float2bfloat16_rn(p - __bfloat162float(h));
+  }
+}
+
+__global__ void __launch_bounds__(1024) accum_loss_kernel(const float* __restrict__ row_loss, int B,
+                                                          double* __restrict__ acc) {
+  __shared__ double sm[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < B; i += 1024) s += static_cast<double>(row_loss[i]);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    acc[0] += sm[0];
+    acc[1] += static_cast<double>(B);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int COLSUM_RS = 32;  // row splits
+// block (32, 8): x = column pair inside a 64-column group, y = row lane
+__global__ void __launch_bounds__(256)
+colsum_stage1_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld,
+                     int rows, float* __restrict__ ws) {
+  __shared__ float sm[8][64];
+  const int col = blockIdx.x * 64 + threadIdx.x * 2;
+  const int rs = blockIdx.y;
+  const int per = (rows + COLSUM_RS - 1) / COLSUM_RS;
+  const int r0 = rs * per, r1 = min(rows, r0 + per);
+  float a0 = 0.f, a1 = 0.f;
+  if (col < ld) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const size_t o = static_cast<size_t>(r) * ld + col;
+      const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + o));
+      a0 += bf_lo(h);
+      a1 += bf_hi(h);
+      if (lo) {
+        const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + o));
+        a0 += bf_lo(l);
+        a1 += bf_hi(l);
+      }
+    }
+  }
+  sm[threadIdx.y][threadIdx.x * 2] = a0;
+  sm[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = threadIdx.x * 2 + k;
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += sm[y][c];
+      if (blockIdx.x * 64 + c < ld) ws[static_cast<size_t>(rs) * ld + blockIdx.x * 64 + c] = s;
+    }
+  }
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ ws, int ld, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < COLSUM_RS; ++r) s += ws[static_cast<size_t>(r) * ld + c];
+  out[c] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+            uint2* __restrict__ w_hi, uint2* __restrict__ w_lo, size_t n4, const double* __restrict__ acc,
+            float lr_t, float b1, float b2, float eps) {
+  const float frames = static_cast<float>(acc[1]);
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 gg = g[i];
+    float4 mm = m[i], vv = v[i], ww = w[i];
+    float gx[4] = {gg.x, gg.y, gg.z, gg.w};
+    float mx[4] = {mm.x, mm.y, mm.z, mm.w};
+    float vx[4] = {vv.x, vv.y, vv.z, vv.w};
+    float wx[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gh = gx[k] / frames;                     // tf.div(grad, num_frames)   trainer.py:174
+      gh = fminf(fmaxf(gh, -1.0f), 1.0f);            // tf.clip_by_value(-1, 1)    trainer.py:178
+      mx[k] += (gh - mx[k]) * omb1;                  // TF ApplyAdam
+      vx[k] += (gh * gh - vx[k]) * omb2;
+      wx[k] -= (mx[k] * lr_t) / (sqrtf(vx[k]) + eps);
+    }
+    m[i] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+    v[i] = make_float4(vx[0], vx[1], vx[2], vx[3]);
+    w[i] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);          // init_grads                 trainer.py:350
+    uint2 h, l;
+    split2(wx[0], wx[1], h.x, l.x);
+    split2(wx[2], wx[3], h.y, l.y);
+    w_hi[i] = h;
+    if (w_lo) w_lo[i] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups,
+                                   int ld, int N, int rows, float eps, float decay,
+                                   float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ mm, float* __restrict__ mv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int gidx = 0; gidx < groups; ++gidx) {
+    s1 += static_cast<double>(ps[static_cast<size_t>(gidx) * ld + c]);
+    s2 += static_cast<double>(pq[static_cast<size_t>(gidx) * ld + c]);
+  }
+  const double mu = s1 / rows;
+  double var = s2 / rows - mu * mu;  // biased (no Bessel), as tf.nn.moments
+  if (var < 0.0) var = 0.0;
+  const float muf = static_cast<float>(mu), varf = static_cast<float>(var);
+  mean[c] = muf;
+  rstd[c] = rsqrtf(varf + eps);
+  if (mm) {  // assign_moving_average: mv -= (1 - decay) * (mv - value)
+    mm[c] -= (1.0f - decay) * (mm[c] - muf);
+    mv[c] -= (1.0f - decay) * (mv[c] - varf);
+  }
+}
+__global__ void bn_eval_stats_kernel(const float* __restrict__ mm, const float* __restrict__ mv, int N,
+                                     float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  mean[c] = mm[c];
+  rstd[c] = rsqrtf(mv[c] + eps);
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t o, float (&x)[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + o));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    x[2 * k] = bf_lo(hw[k]);
+    x[2 * k + 1] = bf_hi(hw[k]);
+  }
+  if (lo) {
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + o));
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[2 * k] += bf_lo(lw[k]);
+      x[2 * k + 1] += bf_hi(lw[k]);
+    }
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t o, const float (&x)[8]) {
+  uint4 h, l;
+  split2(x[0], x[1], h.x, l.x);
+  split2(x[2], x[3], h.y, l.y);
+  split2(x[4], x[5], h.z, l.z);
+  split2(x[6], x[7], h.w, l.w);
+  *reinterpret_cast<uint4*>(hi + o) = h;
+  if (lo) *reinterpret_cast<uint4*>(lo + o) = l;
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
+                int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ beta, int relu, unsigned int drop_thr, float keep_inv,
+                unsigned long long seed, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  const int groups = ld >> 3;
+  const size_t total = static_cast<size_t>(B) * groups;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / groups);
+    const int c = static_cast<int>(i - static_cast<size_t>(r) * groups) << 3;
+    const size_t o = static_cast<size_t>(r) * ld + c;
+    float x[8];
+    load8(z_hi, z_lo, o, x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int col = c + k;
+      float y = 0.f;
+      if (col < N) {
+        y = (x[k] - mean[col]) * rstd[col] + beta[col];
+        if (relu) y = fmaxf(y, 0.f);
+      }
+      x[k] = y;
+    }
+    if (drop_thr != 0u) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(c >> 2) + j, static_cast<uint32_t>(r), 0u, 0u,
+                                          static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+        x[4 * j + 0] = ((rnd.x >> 8) >= drop_thr) ? x[4 * j + 0] * keep_inv : 0.f;
+        x[4 * j + 1] = ((rnd.y >> 8) >= drop_thr) ? x[4 * j + 1] * keep_inv : 0.f;
+        x[4 * j + 2] = ((rnd.z >> 8) >= drop_thr) ? x[4 * j + 2] * keep_inv : 0.f;
+        x[4 * j + 3] = ((rnd.w >> 8) >= drop_thr) ? x[4 * j + 3] * keep_inv : 0.f;
+      }
+    }
+    store8(y_hi, y_lo, o, x);
+  }
+}
+
+// stage 1 of the BN backward column reductions; ws layout [RS][2][ld]
+__global__ void __launch_bounds__(256)
+bn_bwd_stage1_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat16* __restrict__ dy_lo,
+                     const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
+                     int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ ws) {
+  __shared__ float sm[2][8][64];
+  const int col = blockIdx.x * 64 + threadIdx.x * 2;
+  const int rs = blockIdx.y;
+  const int per = (B + COLSUM_RS - 1) / COLSUM_RS;
+  const int r0 = rs * per, r1 = min(B, r0 + per);
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (col < ld) {
+    const float mu0 = col < N ? mean[col] : 0.f, mu1 = col + 1 < N ? mean[col + 1] : 0.f;
+    const float rs0 = col < N ? rstd[col] : 0.f, rs1 = col + 1 < N ? rstd[col + 1] : 0.f;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const size_t o = static_cast<size_t>(r) * ld + col;
+      uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(dy_hi + o));
+      float d0 = bf_lo(w), d1 = bf_hi(w);
+      if (dy_lo) {
+        w = __ldg(reinterpret_cast<const uint32_t*>(dy_lo + o));
+        d0 += bf_lo(w);
+        d1 += bf_hi(w);
+      }
+      w = __ldg(reinterpret_cast<const uint32_t*>(z_hi + o));
+      float z0 = bf_lo(w), z1 = bf_hi(w);
+      if (z_lo) {
+        w = __ldg(reinterpret_cast<const uint32_t*>(z_lo + o));
+        z0 += bf_lo(w);
+        z1 += bf_hi(w);
+      }
+      a0 += d0;
+      a1 += d1;
+      b0 += d0 * ((z0 - mu0) * rs0);
+      b1 += d1 * ((z1 - mu1) * rs1);
+    }
+  }
+  sm[0][threadIdx.y][threadIdx.x * 2] = a0;
+  sm[0][threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  sm[1][threadIdx.y][threadIdx.x * 2] = b0;
+  sm[1][threadIdx.y][threadIdx.x * 2 + 1] = b1;
+  __syncthreads();
+  if (threadIdx.y < 2) {
+    const int which = threadIdx.y;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = threadIdx.x * 2 + k;
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += sm[which][y][c];
+      if (blockIdx.x * 64 + c < ld)
+        ws[(static_cast<size_t>(rs) * 2 + which) * ld + blockIdx.x * 64 + c] = s;
+    }
+  }
+}
+__global__ void bn_bwd_stage2_kernel(const float* __restrict__ ws, int ld, int N, float* __restrict__ sums,
+                                     float* __restrict__ g_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = 0; r < COLSUM_RS; ++r) {
+    s1 += ws[(static_cast<size_t>(r) * 2 + 0) * ld + c];
+    s2 += ws[(static_cast<size_t>(r) * 2 + 1) * ld + c];
+  }
+  sums[c] = s1;
+  sums[ld + c] = s2;
+  g_beta[c] += s1;
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo,
+                    const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
+                    int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ sums) {
+  const int groups = ld >> 3;
+  const size_t total = static_cast<size_t>(B) * groups;
+  const float invB = 1.0f / static_cast<float>(B);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / groups);
+    const int c = static_cast<int>(i - static_cast<size_t>(r) * groups) << 3;
+    const size_t o = static_cast<size_t>(r) * ld + c;
+    float d[8], z[8];
+    load8(dy_hi, dy_lo, o, d);
+    load8(z_hi, z_lo, o, z);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int col = c + k;
+      float dz = 0.f;
+      if (col < N) {
+        const float rsd = rstd[col];
+        const float xh = (z[k] - mean[col]) * rsd;
+        dz = rsd * (d[k] - sums[col] * invB - xh * (sums[ld + col] * invB));
+      }
+      d[k] = dz;
+    }
+    store8(dy_hi, dy_lo, o, d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+decode_out_kernel(const float* __restrict__ logits, int ld, int T, int O, const float* __restrict__ prior,
+                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= T) return;
+  const int nvec = ld >> 2;
+  const float4* zp = reinterpret_cast<const float4*>(logits + static_cast<size_t>(row) * ld);
+  float4 z[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (idx < nvec) {
+      t = __ldg(zp + idx);
+      const int e = idx << 2;
+      if (e + 1 > O) t.x = -INFINITY;
+      if (e + 2 > O) t.y = -INFINITY;
+      if (e + 3 > O) t.z = -INFINITY;
+      if (e + 4 > O) t.w = -INFINITY;
+    }
+    z[i] = t;
+    mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    z[i].x = expf(z[i].x - mx);
+    z[i].y = expf(z[i].y - mx);
+    z[i].z = expf(z[i].z - mx);
+    z[i].w = expf(z[i].w - mx);
+    sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  float* op = out + static_cast<size_t>(row) * O;
+  const bool vec_store = (O & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) << 2;
+    if (e >= O) continue;
+    float p[4] = {z[i].x * inv, z[i].y * inv, z[i].z * inv, z[i].w * inv};
+    if (prior) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e + k < O) p[k] = logf(p[k] / __ldg(prior + e + k));  // np.log(output/prior)  nnet.py:280-286
+    }
+    if (vec_store) {
+      *reinterpret_cast<float4*>(op + e) = make_float4(p[0], p[1], p[2], p[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e + k < O) op[e + k] = p[k];
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+decode_out_generic_kernel(const float* __restrict__ logits, int ld, int T, int O,
+                          const float* __restrict__ prior, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= T) return;
+  const float* zp = logits + static_cast<size_t>(row) * ld;
+  float mx = -INFINITY;
+  for (int e = lane; e < O; e += 32) mx = fmaxf(mx, zp[e]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int e = lane; e < O; e += 32) sum += expf(zp[e] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int e = lane; e < O; e += 32) {
+    float p = expf(zp[e] - mx) * inv;
+    if (prior) p = logf(p / prior[e]);
+    out[static_cast<size_t>(row) * O + e] = p;
+  }
+}
+
+inline int grid_for(size_t work_items, int block, int cap = 148 * 16) {
+  size_t g = (work_items + block - 1) / block;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst, int rows,
+                int cols, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const int vec_ok = (ld_src % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const size_t total = static_cast<size_t>(rows) * (ld_dst >> 2);
+  split_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, ld_src, hi, lo, ld_dst, rows, cols, vec_ok);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int O, float* row_loss,
+                 __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int grid = (B + 7) / 8;
+  if (ld <= 1024)
+    softmax_ce_kernel<8><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+  else if (ld <= 2048)
+    softmax_ce_kernel<16><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+  else if (ld <= 4096)
+    softmax_ce_kernel<32><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+  else
+    softmax_ce_generic_kernel<<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st) {
+  accum_loss_kernel<<<1, 1024, 0, st>>>(row_loss, B, acc);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_colsum_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int rows, int cols, float* ws,
+                  float* out, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  dim3 grid((ld + 63) / 64, COLSUM_RS), block(32, 8);
+  colsum_stage1_kernel<<<grid, block, 0, st>>>(hi, lo, ld, rows, ws);
+  colsum_stage2_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, ld, cols, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, size_t n,
+           const double* acc, float lr_t, float beta1, float beta2, float eps, cudaStream_t st) {
+  const size_t n4 = n >> 2;
+  adam_kernel<<<grid_for(n4, 256, 148 * 8), 256, 0, st>>>(
+      reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(w_hi), reinterpret_cast<uint2*>(w_lo), n4, acc,
+      lr_t, beta1, beta2, eps);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int ld, int N, int rows, float eps,
+                  float decay, float* mean, float* rstd, float* moving_mean, float* moving_var,
+                  cudaStream_t st) {
+  bn_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(part_sum, part_sq, groups, ld, N, rows, eps, decay, mean,
+                                                     rstd, moving_mean, moving_var);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_eval_stats(const float* moving_mean, const float* moving_var, int N, float eps, float* mean,
+                    float* rstd, cudaStream_t st) {
+  bn_eval_stats_kernel<<<(N + 255) / 256, 256, 0, st>>>(moving_mean, moving_var, N, eps, mean, rstd);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
+               const float* rstd, const float* beta, int relu, float keep, unsigned long long seed,
+               __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
+  const size_t total = static_cast<size_t>(B) * (ld >> 3);
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr,
+                                                        1.0f / keep, seed, y_hi, y_lo);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
+                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
+                    float* ws, float* sums, float* g_beta, cudaStream_t st) {
+  dim3 grid((ld + 63) / 64, COLSUM_RS), block(32, 8);
+  bn_bwd_stage1_kernel<<<grid, block, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws);
+  bn_bwd_stage2_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, ld, N, sums, g_beta);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
+                   const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
+                   const float* sums, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const size_t total = static_cast<size_t>(B) * (ld >> 3);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_decode_out(const float* logits, int ld, int T, int O, const float* prior, float* out, cudaStream_t st) {
+  if (T <= 0) return 0;
+  const int grid = (T + 7) / 8;
+  if (ld <= 1024)
+    decode_out_kernel<8><<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+  else if (ld <= 2048)
+    decode_out_kernel<16><<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+  else if (ld <= 4096)
+    decode_out_kernel<32><<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+  else
+    decode_out_generic_kernel<<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace tfk

@@ -1,0 +1,63 @@
+// HBM-bound kernels of the tfkaldi hot path (everything that is not a GEMM).  sm_100a only.
+// Each launcher returns cudaGetLastError() as int (0 = ok).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace tfk {
+
+// fp32 [rows, cols] (pitch ld_src) -> bf16 hi (+ lo = bf16(x - hi) when lo != null), pitch ld_dst.
+int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst,
+                int rows, int cols, cudaStream_t st);
+
+// Softmax cross-entropy forward+backward in one pass over the logits
+// (reference: neuralNetworks/trainer.py:526-531: one_hot + softmax_cross_entropy_with_logits + reduce_sum).
+//   row_loss[r] = logsumexp(z_r) - z_r[label_r]        (0 if the label is outside [0,O): empty one-hot row)
+//   d = softmax(z_r) - onehot(label_r)  -> bf16 hi (+lo), pad columns [O, ld) zeroed.  d_hi may be null.
+int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int O, float* row_loss,
+                 __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, cudaStream_t st);
+
+// acc[0] += sum(row_loss[0..B)) (fixed-order, double);  acc[1] += B
+int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st);
+
+// out[n] += sum over rows of (hi + lo)[row, n]; deterministic two-stage; ws >= 32*ld floats.
+int k_colsum_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int rows, int cols,
+                  float* ws, float* out, cudaStream_t st);
+
+// Mean -> clip[-1,1] -> TF-form Adam -> refresh bf16 shadows -> re-zero the accumulator
+// (reference: neuralNetworks/trainer.py:174-184 and :350).  frames = acc[1] (device double).
+int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, size_t n,
+           const double* acc, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
+
+// Batch-norm (reference: classifiers/activation.py:159 -> tf.contrib.layers.batch_norm defaults):
+// finalize per-column batch statistics from the GEMM epilogue's 32-row partials, update the moving
+// averages (decay 0.999, biased variance), emit mean and rstd = rsqrt(var + eps).
+int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int ld, int N, int rows,
+                  float eps, float decay, float* mean, float* rstd, float* moving_mean,
+                  float* moving_var, cudaStream_t st);
+// mean/rstd from the moving statistics (eval mode)
+int k_bn_eval_stats(const float* moving_mean, const float* moving_var, int N, float eps, float* mean,
+                    float* rstd, cudaStream_t st);
+// y = dropout(relu((z - mean) * rstd + beta)); z,y bf16 hi(+lo) [B, ld]
+int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N,
+               const float* mean, const float* rstd, const float* beta, int relu, float keep,
+               unsigned long long seed, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st);
+// backward: sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat; g_beta += sum_B dy.  ws >= 64*ld floats
+int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
+                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
+                    const float* rstd, float* ws, float* sums, float* g_beta, cudaStream_t st);
+// dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy*xhat)), written in place over dy
+int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
+                   const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
+                   const float* rstd, const float* sums, cudaStream_t st);
+
+// Decoder output (reference: neuralNetworks/decoder.py:44 softmax; nnet.py:280-286 log(P/prior)):
+//   prior == null : out = softmax(z)          (Decoder.__call__)
+//   prior != null : out = log(softmax(z)/prior)   (Nnet.decode pseudo log-likelihood, no flooring)
+// out is dense [T, O] fp32.
+int k_decode_out(const float* logits, int ld, int T, int O, const float* prior, float* out,
+                 cudaStream_t st);
+
+}  // namespace tfk
