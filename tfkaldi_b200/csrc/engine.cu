@@ -1,0 +1,995 @@
+// C-ABI engine (include/tfkaldi_b200.h): owns parameters, optimizer state, activations and TMA plans
+// for one GPU and strings the sm_100a kernels into the reference's train / eval / decode steps.
+//
+// Reference semantics restated here (paths relative to the reference repo):
+//   layer  = matmul + bias -> [batch_norm] -> nonlin -> [dropout]      classifiers/layer.py:52-56,
+//                                                                      classifiers/activation.py:22-42, nnet.py:42-72
+//   output layer: identity, no BN / dropout                            classifiers/dnn.py:67-68, 108-109
+//   loss   = SUM over frames of softmax-CE                             trainer.py:526-531
+//   update = accumulate over micro-batches, /num_frames, clip, Adam    trainer.py:165-184
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tfkaldi_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace tfk;
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+template <typename T>
+inline T* opt(T* base, size_t off) { return base ? base + off : nullptr; }
+
+// ------------------------------------------------------------------ NCCL (resolved at run time)
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  // Prefer the copy already mapped into the process (the one torch.distributed loaded).
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return api;
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(lib, "ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart &&
+           api.GroupEnd;
+  return api;
+}
+constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclSum = 0;
+
+thread_local std::string g_create_error;
+
+struct Layer {
+  int K = 0, N = 0;   // in / out dimension
+  int ldk = 0;        // pitch (elements) of the bf16 input activations
+  int ldn = 0;        // pitch of W rows, output activations, gradient rows: round_up(N, 8)
+  int npad = 0;       // padded length of per-column vectors: round_up(N, 256)
+  bool hidden = false, bn = false;
+  size_t off_w = 0, off_b = 0, off_beta = 0;  // offsets (floats) into the parameter arenas
+  float *moving_mean = nullptr, *moving_var = nullptr;  // [npad]
+  float *bn_mean = nullptr, *bn_rstd = nullptr;          // statistics used by the last forward
+  float* bn_sums = nullptr;                              // [2*ldn] backward column sums
+  __nv_bfloat16 *z_hi = nullptr, *z_lo = nullptr;        // pre-BN linear output [maxB, ldn]
+};
+
+struct Plan {  // TMA descriptors for one (frames, active layers) shape
+  std::vector<GemmParams> fwd_train, fwd_eval, bwd;
+};
+
+}  // namespace
+
+struct tfk_handle {
+  tfk_config cfg;
+  int L = 0;        // hidden layers
+  int active = 0;   // hidden layers in use (layer-wise growth)
+  bool x3 = false;
+  int num_sms = 148;
+  std::vector<Layer> layers;  // L+1
+  size_t arena_n = 0;
+  float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
+  __nv_bfloat16 *Sh = nullptr, *Sl = nullptr;
+  std::vector<__nv_bfloat16*> act_hi, act_lo;  // [L+1]: act[0] = input, act[l+1] = output of hidden l
+  float* logits = nullptr;
+  int ldo = 0, ldh = 0, ld0 = 0, ldmax = 0;
+  __nv_bfloat16 *dzo_hi = nullptr, *dzo_lo = nullptr;
+  __nv_bfloat16 *dA_hi[2] = {nullptr, nullptr}, *dA_lo[2] = {nullptr, nullptr};
+  float* row_loss = nullptr;
+  double* acc = nullptr;  // device {loss_sum, num_frames}
+  double* acc_host = nullptr;
+  float *bn_ps = nullptr, *bn_pq = nullptr;
+  float* ws = nullptr;
+  float* tmp_f32 = nullptr;
+  int* sched = nullptr;
+  std::map<long long, Plan> plans;
+  // trainer scalars
+  long long global_step = 0;
+  double lr_fact = 1.0;
+  unsigned long long drop_seed = 0;
+  // DP
+  void* comm = nullptr;
+  bool own_comm = false;
+  int rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+  // timers
+  bool timers_on = false;
+  struct TimerRec { cudaEvent_t a, b; int cat; };
+  std::vector<TimerRec> timer_recs;
+  std::vector<cudaEvent_t> event_pool;
+  double timer_ms[TFK_NUM_TIMERS] = {0};
+  int64_t timer_launches[TFK_NUM_TIMERS] = {0};
+  int64_t launches = 0;
+  std::string err;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+int fail(tfk_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define TFK_CUDA(h, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(h, TFK_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TFK_LAUNCH(h, expr)                                                                     \
+  do {                                                                                          \
+    int rc_ = (expr);                                                                           \
+    if (rc_ != 0)                                                                               \
+      return fail(h, TFK_ECUDA, "%s failed: %s (%s:%d)", #expr,                                 \
+                  cudaGetErrorString(static_cast<cudaError_t>(rc_)), __FILE__, __LINE__);       \
+  } while (0)
+#define TFK_TRY(expr)          \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != TFK_OK) return rc_; \
+  } while (0)
+
+template <typename T>
+int dev_alloc(tfk_handle* h, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  const size_t bytes = (count ? count : 1) * sizeof(T);
+  TFK_CUDA(h, cudaMalloc(&q, bytes));
+  h->allocs.push_back(q);
+  if (zero) TFK_CUDA(h, cudaMemset(q, 0, bytes));
+  *p = static_cast<T*>(q);
+  return TFK_OK;
+}
+
+struct TimerScope {  // brackets one (or a few) launches with an event pair when timing is on
+  tfk_handle* h;
+  cudaStream_t st;
+  int cat;
+  cudaEvent_t a = nullptr, b = nullptr;
+  TimerScope(tfk_handle* h_, cudaStream_t st_, int cat_, int nlaunch = 1) : h(h_), st(st_), cat(cat_) {
+    h->launches += nlaunch;
+    h->timer_launches[cat] += nlaunch;
+    if (!h->timers_on) return;
+    a = take();
+    b = take();
+    cudaEventRecord(a, st);
+  }
+  ~TimerScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    h->timer_recs.push_back({a, b, cat});
+  }
+  cudaEvent_t take() {
+    if (!h->event_pool.empty()) {
+      cudaEvent_t e = h->event_pool.back();
+      h->event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
+int drain_timers(tfk_handle* h) {
+  for (auto& r : h->timer_recs) {
+    TFK_CUDA(h, cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    TFK_CUDA(h, cudaEventElapsedTime(&ms, r.a, r.b));
+    h->timer_ms[r.cat] += ms;
+    h->event_pool.push_back(r.a);
+    h->event_pool.push_back(r.b);
+  }
+  h->timer_recs.clear();
+  return TFK_OK;
+}
+
+// ------------------------------------------------------------------ plans
+void base_operands(tfk_handle* h, GemmSpec& s) { s.nsplit = h->x3 ? 3 : 1; }
+
+int build_plan(tfk_handle* h, int B, Plan& plan) {
+  const int L = h->L, act = h->active;
+  char err[256] = {0};
+  const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU;
+  const bool drop = h->cfg.keep_prob < 1.0f;
+  plan.fwd_train.assign(L + 1, GemmParams());
+  plan.fwd_eval.assign(L + 1, GemmParams());
+  plan.bwd.assign(L + 1, GemmParams());
+  auto in_of = [&](int l) { return l == L ? act : l; };  // activation index feeding layer l
+  for (int l = 0; l <= L; ++l) {
+    if (l < L && l >= act) continue;
+    const Layer& ly = h->layers[l];
+    const int ai = in_of(l);
+    for (int train = 0; train < 2; ++train) {
+      GemmSpec s;
+      base_operands(h, s);
+      s.M = B; s.N = ly.N; s.K = ly.K;
+      s.A_hi = h->act_hi[ai]; s.A_lo = h->act_lo[ai]; s.lda = ly.ldk; s.a_mn = 0;
+      s.B_hi = h->Sh + ly.off_w; s.B_lo = opt(h->Sl, ly.off_w); s.ldb = ly.ldn; s.b_mn = 1;
+      s.bias = h->P + ly.off_b;
+      if (!ly.hidden) {
+        s.out_kind = OUT_F32; s.D_hi = h->logits; s.ldd = h->ldo;
+      } else if (ly.bn) {
+        s.out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
+        s.D_hi = ly.z_hi; s.D_lo = ly.z_lo; s.ldd = ly.ldn;
+        if (train) { s.stat_sum = h->bn_ps; s.stat_sq = h->bn_pq; s.stat_ld = ly.npad; }
+      } else {
+        s.out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
+        s.D_hi = h->act_hi[l + 1]; s.D_lo = h->act_lo[l + 1]; s.ldd = ly.ldn;
+        s.relu = relu;
+        if (train && drop) { s.keep = h->cfg.keep_prob; s.seed = 0; }
+      }
+      GemmParams& gp = train ? plan.fwd_train[l] : plan.fwd_eval[l];
+      if (gemm_build_params(&s, 1, h->sched, &gp, err, sizeof(err)))
+        return fail(h, TFK_ECUDA, "forward plan layer %d: %s", l, err);
+    }
+    // backward: problem 0 = wgrad (long K first), problem 1 = dgrad into the layer below
+    const __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
+    const __nv_bfloat16* dz_lo = ly.hidden ? h->dA_lo[(L - 1 - l) & 1] : h->dzo_lo;
+    const int ldz = ly.hidden ? ly.ldn : h->ldo;
+    GemmSpec s[2];
+    base_operands(h, s[0]);
+    s[0].M = ly.K; s[0].N = ly.N; s[0].K = B;
+    s[0].A_hi = h->act_hi[ai]; s[0].A_lo = h->act_lo[ai]; s[0].lda = ly.ldk; s[0].a_mn = 1;
+    s[0].B_hi = dz_hi; s[0].B_lo = dz_lo; s[0].ldb = ldz; s[0].b_mn = 1;
+    s[0].out_kind = OUT_F32_REDADD; s[0].D_hi = h->G + ly.off_w; s[0].ldd = ly.ldn;
+    int nspec = 1;
+    if (ai > 0) {
+      // dX[B, K] = dZ[B, N] . W[K, N]^T, masked by the forward output of the layer below
+      const int lower = ai - 1;  // hidden layer that produced act[ai]
+      const int dst = (L - 1 - lower) & 1;  // where layer `lower` expects its dZ
+      base_operands(h, s[1]);
+      s[1].M = B; s[1].N = ly.K; s[1].K = ly.N;
+      s[1].A_hi = dz_hi; s[1].A_lo = dz_lo; s[1].lda = ldz; s[1].a_mn = 0;
+      s[1].B_hi = h->Sh + ly.off_w; s[1].B_lo = opt(h->Sl, ly.off_w); s[1].ldb = ly.ldn; s[1].b_mn = 0;
+      s[1].out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
+      s[1].D_hi = h->dA_hi[dst]; s[1].D_lo = h->dA_lo[dst]; s[1].ldd = h->layers[lower].ldn;
+      if (relu || drop) {
+        s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
+        s[1].mask_nonzero = relu ? 0 : 1;
+        s[1].scale = drop ? 1.0f / h->cfg.keep_prob : 1.0f;
+      }
+      nspec = 2;
+    }
+    if (gemm_build_params(s, nspec, h->sched, &plan.bwd[l], err, sizeof(err)))
+      return fail(h, TFK_ECUDA, "backward plan layer %d: %s", l, err);
+  }
+  return TFK_OK;
+}
+
+int get_plan(tfk_handle* h, int B, Plan** out) {
+  const long long key = static_cast<long long>(B) * 64 + h->active;
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    if (h->plans.size() > 64) h->plans.clear();
+    Plan p;
+    TFK_TRY(build_plan(h, B, p));
+    it = h->plans.emplace(key, std::move(p)).first;
+  }
+  *out = &it->second;
+  return TFK_OK;
+}
+
+int check_frames(tfk_handle* h, int B, const char* what) {
+  if (B <= 0) return fail(h, TFK_ESHAPE, "%s: B=%d must be positive", what, B);
+  if (B > h->cfg.max_frames)
+    return fail(h, TFK_ESHAPE, "%s: B=%d exceeds max_frames=%d", what, B, h->cfg.max_frames);
+  return TFK_OK;
+}
+
+// forward of hidden layers [first, active) and optionally the output layer; input must be in act[first]
+int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bool with_output,
+                  cudaStream_t st) {
+  const int L = h->L;
+  const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU;
+  for (int l = first; l <= L; ++l) {
+    if (l < L && l >= h->active) continue;
+    if (l == L && !with_output) break;
+    Layer& ly = h->layers[l];
+    GemmParams gp = training ? plan.fwd_train[l] : plan.fwd_eval[l];
+    if (training && gp.p[0].drop_thr != 0u) gp.p[0].seed = h->drop_seed + static_cast<unsigned long long>(l);
+    {
+      TimerScope ts(h, st, TFK_TIMER_GEMM_FWD);
+      TFK_LAUNCH(h, gemm_launch(gp, h->num_sms, st));
+    }
+    if (ly.hidden && ly.bn) {
+      TimerScope ts(h, st, TFK_TIMER_BN, 2);
+      if (training) {
+        TFK_LAUNCH(h, k_bn_finalize(h->bn_ps, h->bn_pq, (B + 31) / 32, ly.npad, ly.N, B, h->cfg.bn_eps,
+                                    h->cfg.bn_decay, ly.bn_mean, ly.bn_rstd, ly.moving_mean, ly.moving_var, st));
+      } else {
+        TFK_LAUNCH(h, k_bn_eval_stats(ly.moving_mean, ly.moving_var, ly.N, h->cfg.bn_eps, ly.bn_mean,
+                                      ly.bn_rstd, st));
+      }
+      const float keep = (training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
+      TFK_LAUNCH(h, k_bn_apply(ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd, h->P + ly.off_beta,
+                               relu ? 1 : 0, keep, h->drop_seed + static_cast<unsigned long long>(l),
+                               h->act_hi[l + 1], h->act_lo[l + 1], st));
+    }
+  }
+  return TFK_OK;
+}
+
+// backward of layer l given dZ_l (hidden: in dA[(L-1-l)&1], as d(loss)/d(layer OUTPUT after mask) for BN)
+int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
+                   const GemmParams* gemm_override = nullptr) {
+  const int L = h->L;
+  Layer& ly = h->layers[l];
+  __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
+  __nv_bfloat16* dz_lo = ly.hidden ? h->dA_lo[(L - 1 - l) & 1] : h->dzo_lo;
+  const int ldz = ly.hidden ? ly.ldn : h->ldo;
+  if (ly.hidden && ly.bn) {  // d(bn output) -> d(linear output), plus dbeta
+    TimerScope ts(h, st, TFK_TIMER_BN, 3);
+    TFK_LAUNCH(h, k_bn_bwd_reduce(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
+                                  h->ws, ly.bn_sums, h->G + ly.off_beta, st));
+    TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
+                                 ly.bn_sums, st));
+  }
+  {
+    TimerScope ts(h, st, TFK_TIMER_COLSUM, 2);
+    TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws, h->G + ly.off_b, st));
+  }
+  {
+    TimerScope ts(h, st, TFK_TIMER_GEMM_BWD);
+    TFK_LAUNCH(h, gemm_launch(gemm_override ? *gemm_override : plan.bwd[l], h->num_sms, st));
+  }
+  return TFK_OK;
+}
+
+int load_input(tfk_handle* h, const float* x, int B, int layer_in, cudaStream_t st) {
+  const Layer& ly = h->layers[layer_in == h->L ? h->L : layer_in];
+  const int ai = layer_in == h->L ? h->active : layer_in;
+  TimerScope ts(h, st, TFK_TIMER_CONVERT);
+  TFK_LAUNCH(h, k_split_f32(x, ly.K, h->act_hi[ai], h->act_lo[ai], ly.ldk, B, ly.K, st));
+  return TFK_OK;
+}
+
+int tensor_view(tfk_handle* h, int kind, int layer, float** base, int* rows, int* cols, int* ld) {
+  if (layer < 0 || layer > h->L) return fail(h, TFK_EINVAL, "layer %d out of range [0,%d]", layer, h->L);
+  Layer& ly = h->layers[layer];
+  float* arena = nullptr;
+  int which = 0;  // 0 = W, 1 = b, 2 = beta
+  switch (kind) {
+    case TFK_T_WEIGHTS: arena = h->P; which = 0; break;
+    case TFK_T_BIASES: arena = h->P; which = 1; break;
+    case TFK_T_BN_BETA: arena = h->P; which = 2; break;
+    case TFK_T_ADAM_M_W: arena = h->M; which = 0; break;
+    case TFK_T_ADAM_V_W: arena = h->V; which = 0; break;
+    case TFK_T_ADAM_M_B: arena = h->M; which = 1; break;
+    case TFK_T_ADAM_V_B: arena = h->V; which = 1; break;
+    case TFK_T_ADAM_M_BETA: arena = h->M; which = 2; break;
+    case TFK_T_ADAM_V_BETA: arena = h->V; which = 2; break;
+    case TFK_T_GRAD_W: arena = h->G; which = 0; break;
+    case TFK_T_GRAD_B: arena = h->G; which = 1; break;
+    case TFK_T_GRAD_BETA: arena = h->G; which = 2; break;
+    case TFK_T_BN_MOVING_MEAN:
+    case TFK_T_BN_MOVING_VAR:
+      if (!ly.bn) return fail(h, TFK_EINVAL, "layer %d has no batch-norm state", layer);
+      *base = kind == TFK_T_BN_MOVING_MEAN ? ly.moving_mean : ly.moving_var;
+      *rows = 1; *cols = ly.N; *ld = ly.N;
+      return TFK_OK;
+    default: return fail(h, TFK_EINVAL, "unknown tensor kind %d", kind);
+  }
+  if (which == 0) { *base = arena + ly.off_w; *rows = ly.K; *cols = ly.N; *ld = ly.ldn; }
+  else if (which == 1) { *base = arena + ly.off_b; *rows = 1; *cols = ly.N; *ld = ly.N; }
+  else {
+    if (!ly.bn) return fail(h, TFK_EINVAL, "layer %d has no batch-norm beta", layer);
+    *base = arena + ly.off_beta; *rows = 1; *cols = ly.N; *ld = ly.N;
+  }
+  return TFK_OK;
+}
+
+int refresh_shadow(tfk_handle* h, const Layer& ly, cudaStream_t st) {
+  TimerScope ts(h, st, TFK_TIMER_CONVERT);
+  TFK_LAUNCH(h, k_split_f32(h->P + ly.off_w, ly.ldn, h->Sh + ly.off_w, h->x3 ? h->Sl + ly.off_w : nullptr, ly.ldn,
+                            ly.K, ly.ldn, st));
+  return TFK_OK;
+}
+
+int allreduce_grads(tfk_handle* h, cudaStream_t st) {
+  if (!h->comm || h->nranks <= 1) return TFK_OK;
+  NcclApi& api = nccl();
+  TFK_CUDA(h, cudaEventRecord(h->ev_compute, st));
+  TFK_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+  {
+    TimerScope ts(h, h->comm_stream, TFK_TIMER_ALLREDUCE, 2);
+    int rc = api.GroupStart();
+    // one bucket per layer, output layer first (the order the backward pass finishes them)
+    for (int l = h->L; l >= 0 && rc == 0; --l) {
+      const Layer& ly = h->layers[l];
+      const size_t begin = ly.off_w;
+      const size_t end = (l == h->L) ? h->arena_n : h->layers[l + 1].off_w;
+      rc = api.AllReduce(h->G + begin, h->G + begin, end - begin, kNcclFloat, kNcclSum, h->comm, h->comm_stream);
+    }
+    if (rc == 0) rc = api.AllReduce(h->acc, h->acc, 2, kNcclDouble, kNcclSum, h->comm, h->comm_stream);
+    const int rc2 = api.GroupEnd();
+    if (rc || rc2)
+      return fail(h, TFK_ENCCL, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(rc ? rc : rc2) : "?");
+  }
+  TFK_CUDA(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+  TFK_CUDA(h, cudaStreamWaitEvent(st, h->ev_comm, 0));
+  return TFK_OK;
+}
+
+int ce_and_backward(tfk_handle* h, Plan& plan, const int32_t* labels, int B, bool backward, cudaStream_t st) {
+  {
+    TimerScope ts(h, st, TFK_TIMER_SOFTMAX_CE, 2);
+    TFK_LAUNCH(h, k_softmax_ce(h->logits, h->ldo, labels, B, h->cfg.output_dim, h->row_loss,
+                               backward ? h->dzo_hi : nullptr, (backward && h->x3) ? h->dzo_lo : nullptr, st));
+    TFK_LAUNCH(h, k_accum_loss(h->row_loss, B, h->acc, st));
+  }
+  if (!backward) return TFK_OK;
+  TFK_TRY(backward_layer(h, plan, B, h->L, st));
+  for (int l = h->active - 1; l >= 0; --l) TFK_TRY(backward_layer(h, plan, B, l, st));
+  return TFK_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int tfk_abi_version(void) { return TFK_ABI_VERSION; }
+
+int tfk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void tfk_default_config(tfk_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = TFK_ABI_VERSION;
+  cfg->num_layers = 6;
+  cfg->input_dim = 440;
+  cfg->hidden_dim = 2048;
+  cfg->output_dim = 1936;
+  cfg->max_frames = 8192;
+  cfg->nonlin = TFK_NONLIN_RELU;
+  cfg->batch_norm = 0;
+  cfg->keep_prob = 1.0f;
+  cfg->bn_eps = 1e-3f;
+  cfg->bn_decay = 0.999f;
+  cfg->adam_beta1 = 0.9f;
+  cfg->adam_beta2 = 0.999f;
+  cfg->adam_eps = 1e-8f;
+  cfg->precision = TFK_PREC_BF16;
+  cfg->device = 0;
+  cfg->seed = 0;
+}
+
+const char* tfk_last_error(const tfk_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tfk_destroy(tfk_handle* h) {
+  if (!h) return TFK_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  if (h->comm && h->own_comm && nccl().ok) nccl().CommDestroy(h->comm);
+  for (auto& r : h->timer_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->ev_compute) cudaEventDestroy(h->ev_compute);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->acc_host) cudaFreeHost(h->acc_host);
+  delete h;
+  return TFK_OK;
+}
+
+int tfk_create(const tfk_config* cfg, tfk_handle** out) {
+  if (!cfg || !out) return fail(nullptr, TFK_EINVAL, "tfk_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != TFK_ABI_VERSION)
+    return fail(nullptr, TFK_EINVAL, "tfk_create: abi_version %d != %d", cfg->abi_version, TFK_ABI_VERSION);
+  if (cfg->num_layers < 1 || cfg->num_layers > 62 || cfg->input_dim < 1 || cfg->hidden_dim < 1 ||
+      cfg->output_dim < 1 || cfg->max_frames < 1)
+    return fail(nullptr, TFK_EINVAL, "tfk_create: bad dimensions (L=%d I=%d H=%d O=%d maxB=%d)", cfg->num_layers,
+                cfg->input_dim, cfg->hidden_dim, cfg->output_dim, cfg->max_frames);
+  if (!(cfg->keep_prob > 0.0f))
+    return fail(nullptr, TFK_EINVAL, "tfk_create: keep_prob must be in (0,1] (classifiers/activation.py:127)");
+  if (cfg->nonlin != TFK_NONLIN_RELU && cfg->nonlin != TFK_NONLIN_LINEAR)
+    return fail(nullptr, TFK_EINVAL, "tfk_create: unknown nonlinearity %d (nnet.py:65)", cfg->nonlin);
+  if (cfg->precision != TFK_PREC_BF16 && cfg->precision != TFK_PREC_BF16X3)
+    return fail(nullptr, TFK_EINVAL, "tfk_create: unknown precision %d", cfg->precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, TFK_ECUDA, "tfk_create: no CUDA device available (this engine has no CPU path)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, TFK_EINVAL, "tfk_create: device %d of %d", cfg->device, ndev);
+
+  tfk_handle* h = new tfk_handle();
+  h->cfg = *cfg;
+  if (h->cfg.keep_prob > 1.0f) h->cfg.keep_prob = 1.0f;
+  h->L = cfg->num_layers;
+  h->active = h->L;
+  h->x3 = cfg->precision == TFK_PREC_BF16X3;
+  h->drop_seed = cfg->seed;
+  auto bail = [&](int rc) {
+    g_create_error = h->err;
+    tfk_destroy(h);
+    return rc;
+  };
+#define CREATE_TRY(expr)               \
+  do {                                 \
+    int rc__ = (expr);                 \
+    if (rc__ != TFK_OK) return bail(rc__); \
+  } while (0)
+  {
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
+    if (prop.major != 10)
+      return bail(fail(h, TFK_ECUDA, "device %s is sm_%d%d; this library contains sm_100a code only", prop.name,
+                       prop.major, prop.minor));
+    h->num_sms = prop.multiProcessorCount;
+    const int rc = gemm_init();
+    if (rc) return bail(fail(h, TFK_ECUDA, "gemm_init: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))));
+  }
+  const int L = h->L, maxB = cfg->max_frames;
+  h->layers.resize(L + 1);
+  size_t off = 0;
+  for (int l = 0; l <= L; ++l) {
+    Layer& ly = h->layers[l];
+    ly.hidden = l < L;
+    ly.K = (l == 0) ? cfg->input_dim : cfg->hidden_dim;
+    ly.N = ly.hidden ? cfg->hidden_dim : cfg->output_dim;
+    ly.ldk = round_up(ly.K, 8);
+    ly.ldn = round_up(ly.N, 8);
+    ly.npad = round_up(ly.N, 256);
+    ly.bn = ly.hidden && cfg->batch_norm;
+    ly.off_w = off; off += static_cast<size_t>(ly.K) * ly.ldn;
+    ly.off_b = off; off += ly.npad;
+    if (ly.bn) { ly.off_beta = off; off += ly.npad; }
+  }
+  h->arena_n = (off + 3) / 4 * 4;
+  h->ld0 = h->layers[0].ldk;
+  h->ldh = round_up(cfg->hidden_dim, 8);
+  h->ldo = round_up(cfg->output_dim, 8);
+  h->ldmax = h->ldh > h->ldo ? h->ldh : h->ldo;
+  if (h->ld0 > h->ldmax) h->ldmax = h->ld0;
+  CREATE_TRY(dev_alloc(h, &h->P, h->arena_n));
+  CREATE_TRY(dev_alloc(h, &h->G, h->arena_n));
+  CREATE_TRY(dev_alloc(h, &h->M, h->arena_n));
+  CREATE_TRY(dev_alloc(h, &h->V, h->arena_n));
+  CREATE_TRY(dev_alloc(h, &h->Sh, h->arena_n));
+  if (h->x3) CREATE_TRY(dev_alloc(h, &h->Sl, h->arena_n));
+  h->act_hi.assign(L + 1, nullptr);
+  h->act_lo.assign(L + 1, nullptr);
+  for (int l = 0; l <= L; ++l) {
+    const size_t n = static_cast<size_t>(maxB) * (l == 0 ? h->ld0 : h->ldh);
+    CREATE_TRY(dev_alloc(h, &h->act_hi[l], n));
+    if (h->x3) CREATE_TRY(dev_alloc(h, &h->act_lo[l], n));
+  }
+  for (int l = 0; l < L; ++l) {
+    Layer& ly = h->layers[l];
+    if (!ly.bn) continue;
+    CREATE_TRY(dev_alloc(h, &ly.z_hi, static_cast<size_t>(maxB) * ly.ldn));
+    if (h->x3) CREATE_TRY(dev_alloc(h, &ly.z_lo, static_cast<size_t>(maxB) * ly.ldn));
+    CREATE_TRY(dev_alloc(h, &ly.moving_mean, ly.npad));
+    CREATE_TRY(dev_alloc(h, &ly.moving_var, ly.npad));
+    CREATE_TRY(dev_alloc(h, &ly.bn_mean, ly.npad));
+    CREATE_TRY(dev_alloc(h, &ly.bn_rstd, ly.npad));
+    CREATE_TRY(dev_alloc(h, &ly.bn_sums, 2 * static_cast<size_t>(ly.ldn)));
+    std::vector<float> ones(ly.npad, 1.0f);  // moving_variance initialises to 1 (tf.contrib.layers.batch_norm)
+    cudaError_t e = cudaMemcpy(ly.moving_var, ones.data(), ly.npad * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "init moving_var: %s", cudaGetErrorString(e)));
+  }
+  CREATE_TRY(dev_alloc(h, &h->logits, static_cast<size_t>(maxB) * h->ldo));
+  CREATE_TRY(dev_alloc(h, &h->dzo_hi, static_cast<size_t>(maxB) * h->ldo));
+  if (h->x3) CREATE_TRY(dev_alloc(h, &h->dzo_lo, static_cast<size_t>(maxB) * h->ldo));
+  for (int i = 0; i < 2; ++i) {
+    CREATE_TRY(dev_alloc(h, &h->dA_hi[i], static_cast<size_t>(maxB) * h->ldh));
+    if (h->x3) CREATE_TRY(dev_alloc(h, &h->dA_lo[i], static_cast<size_t>(maxB) * h->ldh));
+  }
+  CREATE_TRY(dev_alloc(h, &h->row_loss, maxB));
+  CREATE_TRY(dev_alloc(h, &h->acc, 2));
+  if (cfg->batch_norm) {
+    const size_t n = static_cast<size_t>(maxB / 32 + 8) * round_up(cfg->hidden_dim, 256);
+    CREATE_TRY(dev_alloc(h, &h->bn_ps, n));
+    CREATE_TRY(dev_alloc(h, &h->bn_pq, n));
+  }
+  CREATE_TRY(dev_alloc(h, &h->ws, 64 * static_cast<size_t>(h->ldmax)));
+  CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
+  CREATE_TRY(dev_alloc(h, &h->sched, 2));
+  {
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->acc_host), 2 * sizeof(double));
+    if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "cudaMallocHost: %s", cudaGetErrorString(e)));
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "create sync: %s", cudaGetErrorString(e)));
+  }
+#undef CREATE_TRY
+  *out = h;
+  return TFK_OK;
+}
+
+int tfk_set_tensor(tfk_handle* h, int kind, int layer, const float* src, size_t count, void* stream) {
+  if (!h || !src) return fail(h, TFK_EINVAL, "tfk_set_tensor: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* base; int rows, cols, ld;
+  TFK_TRY(tensor_view(h, kind, layer, &base, &rows, &cols, &ld));
+  if (count != static_cast<size_t>(rows) * cols)
+    return fail(h, TFK_ESHAPE, "tfk_set_tensor: kind %d layer %d expects %d x %d elements, got %zu", kind, layer, rows, cols, count);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  TFK_CUDA(h, cudaMemcpy2DAsync(base, static_cast<size_t>(ld) * 4, src, static_cast<size_t>(cols) * 4,
+                                static_cast<size_t>(cols) * 4, rows, cudaMemcpyDefault, st));
+  if (kind == TFK_T_WEIGHTS) TFK_TRY(refresh_shadow(h, h->layers[layer], st));
+  TFK_CUDA(h, cudaStreamSynchronize(st));  // src may be pageable host memory owned by the caller
+  return TFK_OK;
+}
+
+int tfk_get_tensor(tfk_handle* h, int kind, int layer, float* dst, size_t count, void* stream) {
+  if (!h || !dst) return fail(h, TFK_EINVAL, "tfk_get_tensor: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* base; int rows, cols, ld;
+  TFK_TRY(tensor_view(h, kind, layer, &base, &rows, &cols, &ld));
+  if (count != static_cast<size_t>(rows) * cols)
+    return fail(h, TFK_ESHAPE, "tfk_get_tensor: kind %d layer %d holds %d x %d elements, asked %zu", kind, layer, rows, cols, count);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  TFK_CUDA(h, cudaMemcpy2DAsync(dst, static_cast<size_t>(cols) * 4, base, static_cast<size_t>(ld) * 4,
+                                static_cast<size_t>(cols) * 4, rows, cudaMemcpyDefault, st));
+  TFK_CUDA(h, cudaStreamSynchronize(st));
+  return TFK_OK;
+}
+
+int tfk_set_scalar(tfk_handle* h, int kind, double value) {
+  if (!h) return TFK_EINVAL;
+  switch (kind) {
+    case TFK_S_GLOBAL_STEP: h->global_step = static_cast<long long>(value); return TFK_OK;
+    case TFK_S_LR_FACT: h->lr_fact = value; return TFK_OK;
+    case TFK_S_ACTIVE_LAYERS: return tfk_set_active_layers(h, static_cast<int>(value));
+    default: return fail(h, TFK_EINVAL, "tfk_set_scalar: kind %d is not writable", kind);
+  }
+}
+
+int tfk_get_scalar(tfk_handle* h, int kind, double* value_host, void* stream) {
+  if (!h || !value_host) return fail(h, TFK_EINVAL, "tfk_get_scalar: null argument");
+  switch (kind) {
+    case TFK_S_GLOBAL_STEP: *value_host = static_cast<double>(h->global_step); return TFK_OK;
+    case TFK_S_LR_FACT: *value_host = h->lr_fact; return TFK_OK;
+    case TFK_S_ACTIVE_LAYERS: *value_host = h->active; return TFK_OK;
+    case TFK_S_LOSS_SUM:
+    case TFK_S_NUM_FRAMES: {
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      TFK_CUDA(h, cudaStreamSynchronize(st));
+      *value_host = h->acc_host[kind == TFK_S_LOSS_SUM ? 0 : 1];
+      return TFK_OK;
+    }
+    default: return fail(h, TFK_EINVAL, "tfk_get_scalar: unknown kind %d", kind);
+  }
+}
+
+int tfk_halve_lr(tfk_handle* h) {
+  if (!h) return TFK_EINVAL;
+  h->lr_fact *= 0.5;  // learning_rate_fact.assign(learning_rate_fact/2)   trainer.py:141-142
+  return TFK_OK;
+}
+
+int tfk_set_active_layers(tfk_handle* h, int n) {
+  if (!h) return TFK_EINVAL;
+  if (n < 1 || n > h->L) return fail(h, TFK_EINVAL, "tfk_set_active_layers: %d not in [1,%d]", n, h->L);
+  h->active = n;
+  return TFK_OK;
+}
+
+int tfk_set_dropout_seed(tfk_handle* h, uint64_t seed) {
+  if (!h) return TFK_EINVAL;
+  h->drop_seed = seed;
+  return TFK_OK;
+}
+
+int tfk_fflayer_fwd(tfk_handle* h, int layer, const float* x, float* y, int B, int training, void* stream) {
+  if (!h || !x || !y) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: null argument");
+  if (layer < 0 || layer > h->L) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: layer %d", layer);
+  if (layer < h->L && layer >= h->active) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: layer %d is not active", layer);
+  TFK_TRY(check_frames(h, B, "tfk_fflayer_fwd"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, B, &plan));
+  TFK_TRY(load_input(h, x, B, layer, st));
+  Layer& ly = h->layers[layer];
+  // run exactly this layer
+  const int saved_active = h->active;
+  if (layer < h->L) {
+    GemmParams gp = training ? plan->fwd_train[layer] : plan->fwd_eval[layer];
+    // reuse forward_range for the BN tail by temporarily narrowing the range
+    h->active = layer + 1;
+    int rc = forward_range(h, *plan, B, training != 0, layer, false, st);
+    h->active = saved_active;
+    (void)gp;
+    TFK_TRY(rc);
+    TimerScope ts(h, st, TFK_TIMER_CONVERT);
+    TFK_LAUNCH(h, k_merge_bf16(h->act_hi[layer + 1], h->act_lo[layer + 1], ly.ldn, y, ly.N, B, ly.N, st));
+  } else {
+    {
+      TimerScope ts(h, st, TFK_TIMER_GEMM_FWD);
+      TFK_LAUNCH(h, gemm_launch(training ? plan->fwd_train[layer] : plan->fwd_eval[layer], h->num_sms, st));
+    }
+    TFK_CUDA(h, cudaMemcpy2DAsync(y, static_cast<size_t>(ly.N) * 4, h->logits, static_cast<size_t>(h->ldo) * 4,
+                                  static_cast<size_t>(ly.N) * 4, B, cudaMemcpyDeviceToDevice, st));
+  }
+  return TFK_OK;
+}
+
+int tfk_fflayer_bwd(tfk_handle* h, int layer, const float* dy, float* dx, int B, void* stream) {
+  if (!h || !dy) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: null argument");
+  if (layer < 0 || layer > h->L) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: layer %d", layer);
+  if (layer < h->L && layer >= h->active) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: layer %d is not active", layer);
+  TFK_TRY(check_frames(h, B, "tfk_fflayer_bwd"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, B, &plan));
+  Layer& ly = h->layers[layer];
+  const int L = h->L;
+  const int ai = layer == L ? h->active : layer;
+  if (dx && ai == 0) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: layer 0 has no dx (the reference never forms d/d input)");
+  __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - layer) & 1] : h->dzo_hi;
+  __nv_bfloat16* dz_lo = ly.hidden ? h->dA_lo[(L - 1 - layer) & 1] : h->dzo_lo;
+  const int ldz = ly.hidden ? ly.ldn : h->ldo;
+  {
+    // (1) the layer's own activation chain, backward: relu / dropout mask from the stored forward output
+    TimerScope ts(h, st, TFK_TIMER_CONVERT, 3);
+    const float* src = dy;
+    const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU, drop = h->cfg.keep_prob < 1.0f;
+    if (ly.hidden && (relu || drop)) {
+      TFK_LAUNCH(h, k_merge_bf16(h->act_hi[layer + 1], h->act_lo[layer + 1], ly.ldn, h->tmp_f32, ly.N, B, ly.N, st));
+      TFK_LAUNCH(h, k_mask_scale_f32(dy, h->tmp_f32, h->tmp_f32, static_cast<size_t>(B) * ly.N,
+                                     drop ? 1.0f / h->cfg.keep_prob : 1.0f, relu ? 0 : 1, st));
+      src = h->tmp_f32;
+    }
+    TFK_LAUNCH(h, k_split_f32(src, ly.N, dz_hi, h->x3 ? dz_lo : nullptr, ldz, B, ly.N, st));
+  }
+  // (2) [BN backward] + dbias + wgrad, and (3) the raw dgrad dx = dz . W^T (no mask of the layer below)
+  GemmSpec s[2];
+  s[0].nsplit = s[1].nsplit = h->x3 ? 3 : 1;
+  s[0].M = ly.K; s[0].N = ly.N; s[0].K = B;
+  s[0].A_hi = h->act_hi[ai]; s[0].A_lo = h->act_lo[ai]; s[0].lda = ly.ldk; s[0].a_mn = 1;
+  s[0].B_hi = dz_hi; s[0].B_lo = dz_lo; s[0].ldb = ldz; s[0].b_mn = 1;
+  s[0].out_kind = OUT_F32_REDADD; s[0].D_hi = h->G + ly.off_w; s[0].ldd = ly.ldn;
+  const int dst = (L - layer) & 1;  // any dA buffer other than the one holding dz
+  if (dx) {
+    s[1].M = B; s[1].N = ly.K; s[1].K = ly.N;
+    s[1].A_hi = dz_hi; s[1].A_lo = dz_lo; s[1].lda = ldz; s[1].a_mn = 0;
+    s[1].B_hi = h->Sh + ly.off_w; s[1].B_lo = opt(h->Sl, ly.off_w); s[1].ldb = ly.ldn; s[1].b_mn = 0;
+    s[1].out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
+    s[1].D_hi = h->dA_hi[dst]; s[1].D_lo = h->dA_lo[dst]; s[1].ldd = ly.ldk;
+  }
+  GemmParams gp;
+  char err[256] = {0};
+  if (gemm_build_params(s, dx ? 2 : 1, h->sched, &gp, err, sizeof(err)))
+    return fail(h, TFK_ECUDA, "tfk_fflayer_bwd plan: %s", err);
+  TFK_TRY(backward_layer(h, *plan, B, layer, st, &gp));
+  if (dx) {
+    TimerScope ts(h, st, TFK_TIMER_CONVERT);
+    TFK_LAUNCH(h, k_merge_bf16(h->dA_hi[dst], h->dA_lo[dst], ly.ldk, dx, ly.K, B, ly.K, st));
+  }
+  return TFK_OK;
+}
+
+int tfk_softmax_ce(tfk_handle* h, const float* logits, const int32_t* labels, int B, float* loss_sum,
+                   float* dlogits, void* stream) {
+  if (!h || !logits || !labels || !loss_sum) return fail(h, TFK_EINVAL, "tfk_softmax_ce: null argument");
+  TFK_TRY(check_frames(h, B, "tfk_softmax_ce"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int O = h->cfg.output_dim;
+  TFK_CUDA(h, cudaMemcpy2DAsync(h->logits, static_cast<size_t>(h->ldo) * 4, logits, static_cast<size_t>(O) * 4,
+                                static_cast<size_t>(O) * 4, B, cudaMemcpyDeviceToDevice, st));
+  {
+    TimerScope ts(h, st, TFK_TIMER_SOFTMAX_CE);
+    // full-precision gradient for the stand-alone entry: always emit hi+lo
+    __nv_bfloat16* lo = h->x3 ? h->dzo_lo : reinterpret_cast<__nv_bfloat16*>(h->tmp_f32);
+    TFK_LAUNCH(h, k_softmax_ce(h->logits, h->ldo, labels, B, O, h->row_loss, h->dzo_hi, lo, st));
+    if (dlogits) TFK_LAUNCH(h, k_merge_bf16(h->dzo_hi, lo, h->ldo, dlogits, O, B, O, st));
+  }
+  // loss_sum = sum(row_loss): reuse the deterministic reducer on a scratch accumulator
+  double* scratch = reinterpret_cast<double*>(h->ws);
+  TFK_CUDA(h, cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st));
+  TFK_LAUNCH(h, k_accum_loss(h->row_loss, B, scratch, st));
+  TFK_LAUNCH(h, k_double_to_float(scratch, loss_sum, st));
+  h->launches += 2;
+  return TFK_OK;
+}
+
+int tfk_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, void* stream) {
+  if (!h || !x || !labels) return fail(h, TFK_EINVAL, "tfk_accumulate: null argument");
+  TFK_TRY(check_frames(h, B, "tfk_accumulate"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, B, &plan));
+  TFK_TRY(load_input(h, x, B, 0, st));
+  TFK_TRY(forward_range(h, *plan, B, true, 0, true, st));
+  TFK_TRY(ce_and_backward(h, *plan, labels, B, true, st));
+  h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  return TFK_OK;
+}
+
+int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
+  if (!h) return TFK_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  TFK_TRY(allreduce_grads(h, st));
+  h->global_step += 1;  // apply_gradients(global_step=...)   trainer.py:182-184
+  const double t = static_cast<double>(h->global_step);
+  const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+  const double lr_eff = static_cast<double>(lr) * h->lr_fact;
+  const float lr_t = static_cast<float>(lr_eff * std::sqrt(1.0 - std::pow(b2, t)) / (1.0 - std::pow(b1, t)));
+  {
+    TimerScope ts(h, st, TFK_TIMER_ADAM);
+    TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, h->arena_n, h->acc, lr_t,
+                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
+  }
+  TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));  // init_loss / init_num_frames
+  if (mean_loss_host) {
+    TFK_CUDA(h, cudaStreamSynchronize(st));
+    *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);  // average_loss   trainer.py:198
+  }
+  return TFK_OK;
+}
+
+int tfk_eval_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, void* stream) {
+  if (!h || !x || !labels) return fail(h, TFK_EINVAL, "tfk_eval_accumulate: null argument");
+  TFK_TRY(check_frames(h, B, "tfk_eval_accumulate"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, B, &plan));
+  TFK_TRY(load_input(h, x, B, 0, st));
+  TFK_TRY(forward_range(h, *plan, B, false, 0, true, st));
+  TFK_TRY(ce_and_backward(h, *plan, labels, B, false, st));
+  return TFK_OK;
+}
+
+int tfk_eval_finish(tfk_handle* h, float* mean_loss_host, void* stream) {
+  if (!h || !mean_loss_host) return fail(h, TFK_EINVAL, "tfk_eval_finish: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));
+  TFK_CUDA(h, cudaStreamSynchronize(st));
+  *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
+  return TFK_OK;
+}
+
+static int forward_decode(tfk_handle* h, const float* x, int T, const float* prior, float* out, cudaStream_t st) {
+  if (T <= 0) return fail(h, TFK_ESHAPE, "decode: T=%d must be positive", T);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int I = h->cfg.input_dim, O = h->cfg.output_dim, maxB = h->cfg.max_frames;
+  for (int t0 = 0; t0 < T; t0 += maxB) {  // frames are independent: tile long utterances over the workspace
+    const int B = (T - t0 < maxB) ? (T - t0) : maxB;
+    Plan* plan;
+    TFK_TRY(get_plan(h, B, &plan));
+    TFK_TRY(load_input(h, x + static_cast<size_t>(t0) * I, B, 0, st));
+    TFK_TRY(forward_range(h, *plan, B, false, 0, true, st));
+    TimerScope ts(h, st, TFK_TIMER_DECODE_OUT);
+    TFK_LAUNCH(h, k_decode_out(h->logits, h->ldo, B, O, prior, out + static_cast<size_t>(t0) * O, st));
+  }
+  return TFK_OK;
+}
+
+int tfk_forward_posteriors(tfk_handle* h, const float* x, int T, float* out, void* stream) {
+  if (!h || !x || !out) return fail(h, TFK_EINVAL, "tfk_forward_posteriors: null argument");
+  return forward_decode(h, x, T, nullptr, out, static_cast<cudaStream_t>(stream));
+}
+
+int tfk_forward_loglik(tfk_handle* h, const float* x, int T, const float* prior, float* out, void* stream) {
+  if (!h || !x || !out || !prior) return fail(h, TFK_EINVAL, "tfk_forward_loglik: null argument");
+  return forward_decode(h, x, T, prior, out, static_cast<cudaStream_t>(stream));
+}
+
+int tfk_comm_unique_id(uint8_t* id128_host) {
+  if (!id128_host) return TFK_EINVAL;
+  NcclApi& api = nccl();
+  if (!api.ok) return fail(nullptr, TFK_ENCCL, "libnccl.so.2 not available");
+  NcclApi::UniqueId id;
+  const int rc = api.GetUniqueId(&id);
+  if (rc) return fail(nullptr, TFK_ENCCL, "ncclGetUniqueId failed (%d)", rc);
+  memcpy(id128_host, id.internal, 128);
+  return TFK_OK;
+}
+
+static int setup_comm_streams(tfk_handle* h) {
+  if (!h->comm_stream) {
+    TFK_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    TFK_CUDA(h, cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
+    TFK_CUDA(h, cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+  }
+  return TFK_OK;
+}
+
+int tfk_comm_init(tfk_handle* h, const uint8_t* id128_host, int rank, int nranks) {
+  if (!h || !id128_host) return fail(h, TFK_EINVAL, "tfk_comm_init: null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, TFK_EINVAL, "tfk_comm_init: rank %d of %d", rank, nranks);
+  NcclApi& api = nccl();
+  if (!api.ok) return fail(h, TFK_ENCCL, "libnccl.so.2 not available");
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  NcclApi::UniqueId id;
+  memcpy(id.internal, id128_host, 128);
+  void* comm = nullptr;
+  const int rc = api.CommInitRank(&comm, nranks, id, rank);
+  if (rc) return fail(h, TFK_ENCCL, "ncclCommInitRank failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+  h->comm = comm;
+  h->own_comm = true;
+  h->rank = rank;
+  h->nranks = nranks;
+  return setup_comm_streams(h);
+}
+
+int tfk_set_comm(tfk_handle* h, void* nccl_comm, int rank, int nranks) {
+  if (!h) return TFK_EINVAL;
+  if (nccl_comm && !nccl().ok) return fail(h, TFK_ENCCL, "libnccl.so.2 not available");
+  h->comm = nccl_comm;
+  h->own_comm = false;
+  h->rank = rank;
+  h->nranks = nccl_comm ? nranks : 1;
+  return nccl_comm ? setup_comm_streams(h) : TFK_OK;
+}
+
+int tfk_enable_timers(tfk_handle* h, int on) {
+  if (!h) return TFK_EINVAL;
+  TFK_TRY(drain_timers(h));
+  h->timers_on = on != 0;
+  if (on) {
+    for (int i = 0; i < TFK_NUM_TIMERS; ++i) { h->timer_ms[i] = 0; h->timer_launches[i] = 0; }
+  }
+  return TFK_OK;
+}
+
+int tfk_get_timers(tfk_handle* h, double* ms_total, int64_t* launches) {
+  if (!h) return TFK_EINVAL;
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  TFK_TRY(drain_timers(h));
+  for (int i = 0; i < TFK_NUM_TIMERS; ++i) {
+    if (ms_total) ms_total[i] = h->timer_ms[i];
+    if (launches) launches[i] = h->timer_launches[i];
+  }
+  return TFK_OK;
+}
+
+int64_t tfk_kernel_launches(const tfk_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

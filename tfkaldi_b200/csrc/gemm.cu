@@ -160,8 +160,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
           for (int k = 0; k < 4; ++k) {
             // bf16 > 0  <=>  sign bit clear and magnitude non-zero
             const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
-            const bool plo = (lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0;
-            const bool phi = (hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0;
+            const bool plo = (pr.mask_nonzero || (lo & 0x8000u) == 0) && (lo & 0x7FFFu) != 0;
+            const bool phi = (pr.mask_nonzero || (hi & 0x8000u) == 0) && (hi & 0x7FFFu) != 0;
             v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * pr.scale : 0.f;
             v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * pr.scale : 0.f;
           }
@@ -171,7 +171,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         for (int j = 0; j < 32; ++j) {
           const bool ok = row_ok && (col0 + j) < pr.N;
           const float mv = ok ? __bfloat162float(mp[j]) : 0.f;
-          v[j] = (mv > 0.f) ? v[j] * pr.scale : 0.f;
+          v[j] = (pr.mask_nonzero ? (mv != 0.f) : (mv > 0.f)) ? v[j] * pr.scale : 0.f;
         }
       }
     }
@@ -604,6 +604,7 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.out_kind = s.out_kind;
     p.relu = s.relu;
     p.mask_ld = s.mask_ld;
+    p.mask_nonzero = s.mask_nonzero;
     p.scale = s.scale;
     p.keep_inv = 1.0f / s.keep;
     p.drop_thr = (s.keep < 1.0f) ? dropout_threshold(s.keep) : 0u;

@@ -49,8 +49,9 @@ struct GemmSpec {
   int ldd = 0;
   const float* bias = nullptr;  // [>= roundup(N,256)] added per column, or null
   int relu = 0;
-  const __nv_bfloat16* mask_src = nullptr;  // [M, mask_ld]: v = mask_src>0 ? v*scale : 0
+  const __nv_bfloat16* mask_src = nullptr;  // [M, mask_ld]: v = pass(mask_src) ? v*scale : 0
   int mask_ld = 0;
+  int mask_nonzero = 0;  // 0: pass where mask_src > 0 (relu);  1: pass where mask_src != 0 (linear+dropout)
   float scale = 1.0f;
   // forward dropout (reference: classifiers/activation.py:140-141): keep<1 => v = v/keep * floor(keep+u)
   float keep = 1.0f;
@@ -67,7 +68,7 @@ struct alignas(64) GemmProblem {
   CUtensorMap tmD[2];
   int M, N, K;
   int a_mn, b_mn, nsplit, out_kind;
-  int relu, mask_ld;
+  int relu, mask_ld, mask_nonzero;
   float scale, keep_inv;
   unsigned int drop_thr;  // keep element iff (philox >> 8) >= drop_thr; 0 => no dropout
   const float* bias;

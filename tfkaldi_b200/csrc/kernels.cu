@@ -62,6 +62,32 @@ __global__ void split_f32_kernel(const float* __restrict__ src, int ld_src, __nv
   }
 }
 
+__global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                  int ld_src, float* __restrict__ dst, int ld_dst, int rows, int cols) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols);
+    const int c = static_cast<int>(i - static_cast<size_t>(r) * cols);
+    float v = __bfloat162float(hi[static_cast<size_t>(r) * ld_src + c]);
+    if (lo) v += __bfloat162float(lo[static_cast<size_t>(r) * ld_src + c]);
+    dst[static_cast<size_t>(r) * ld_dst + c] = v;
+  }
+}
+
+__global__ void mask_scale_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                      float* __restrict__ out, size_t n, float scale, int nonzero) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float yy = y[i];
+    const bool pass = nonzero ? (yy != 0.f) : (yy > 0.f);
+    out[i] = pass ? dy[i] * scale : 0.f;
+  }
+}
+__global__ void double_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst) {
+  dst[0] = static_cast<float>(src[0]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // One warp per row; the row lives in registers (NV float4 per lane) so logits are read once.
 template <int NV>
@@ -553,6 +579,25 @@ int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* 
   const int vec_ok = (ld_src % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   const size_t total = static_cast<size_t>(rows) * (ld_dst >> 2);
   split_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, ld_src, hi, lo, ld_dst, rows, cols, vec_ok);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_merge_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld_src, float* dst, int ld_dst,
+                 int rows, int cols, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  merge_bf16_kernel<<<grid_for(static_cast<size_t>(rows) * cols, 256), 256, 0, st>>>(hi, lo, ld_src, dst,
+                                                                                   ld_dst, rows, cols);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_mask_scale_f32(const float* dy, const float* y, float* out, size_t n, float scale, int nonzero,
+                     cudaStream_t st) {
+  if (n == 0) return 0;
+  mask_scale_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(dy, y, out, n, scale, nonzero);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_double_to_float(const double* src, float* dst, cudaStream_t st) {
+  double_to_float_kernel<<<1, 1, 0, st>>>(src, dst);
   return static_cast<int>(cudaGetLastError());
 }
 

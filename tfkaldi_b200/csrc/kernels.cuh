@@ -12,6 +12,16 @@ namespace tfk {
 int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst,
                 int rows, int cols, cudaStream_t st);
 
+// bf16 hi (+lo) [rows, ld_src] -> fp32 [rows, cols] (pitch ld_dst): dst = hi + lo
+int k_merge_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld_src, float* dst, int ld_dst,
+                 int rows, int cols, cudaStream_t st);
+
+// out[i] = pass(y[i]) ? dy[i] * scale : 0, pass = (y > 0) or (y != 0): activation-chain backward on fp32
+int k_mask_scale_f32(const float* dy, const float* y, float* out, size_t n, float scale, int nonzero,
+                     cudaStream_t st);
+// dst[0] = (float)src[0]
+int k_double_to_float(const double* src, float* dst, cudaStream_t st);
+
 // Softmax cross-entropy forward+backward in one pass over the logits
 // (reference: neuralNetworks/trainer.py:526-531: one_hot + softmax_cross_entropy_with_logits + reduce_sum).
 //   row_loss[r] = logsumexp(z_r) - z_r[label_r]        (0 if the label is outside [0,O): empty one-hot row)

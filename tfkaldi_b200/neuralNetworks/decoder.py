@@ -1,0 +1,46 @@
+"""Decoding environment with the reference's Decoder API (reference: neuralNetworks/decoder.py).
+
+`Decoder(classifier, input_dim, max_length)(inputs)` returned softmax posteriors from
+`outputs.eval(feed)` on the utterance padded to max_length (decoder.py:49-71); here it is one
+tfk_forward_posteriors call on the unpadded frames.  `loglik` additionally fuses Nnet.decode's
+host-side `np.log(output / prior)` (nnet.py:280-286) into the output kernel."""
+import numpy as np
+import torch
+
+from ..engine import Engine
+
+
+class Decoder(object):
+    def __init__(self, classifier, input_dim, max_length, *, precision="bf16", device=None, max_frames=16384):
+        spec = classifier.engine_spec(input_dim)
+        self.max_length = max_length
+        self.input_dim = input_dim
+        self.engine = Engine(spec["num_layers"], spec["input_dim"], spec["hidden_dim"], spec["output_dim"],
+                             min(int(max_frames), max(int(max_length), 1)), nonlin=spec["nonlin"],
+                             batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"], precision=precision, device=device)
+        self._trainer_like = None
+
+    def __call__(self, inputs):
+        """[N, F] numpy -> [N, O] numpy posteriors (eval mode: moving-stat batch norm, no dropout)"""
+        return self.engine.posteriors(np.ascontiguousarray(inputs, dtype=np.float32)).cpu().numpy()
+
+    def loglik(self, inputs, prior, out=None):
+        """device tensor [N, O] = log(softmax / prior), no flooring (nnet.py:280-286)"""
+        return self.engine.loglik(inputs, prior, out=out)
+
+    def restore(self, filename):
+        """load the model written by Trainer.save_model (decoder.py:73-81)"""
+        from .trainer import Trainer
+
+        path = Trainer._path(filename)
+        names = {"parameters/weights": "W", "parameters/biases": "b", "activation/batch_norm/beta": "beta",
+                 "activation/batch_norm/moving_mean": "moving_mean", "activation/batch_norm/moving_variance": "moving_var"}
+        params = {}
+        with np.load(path) as arrays:
+            for key in arrays.files:
+                if key == "Classifier/initialisedlayers":
+                    self.engine.set_active_layers(int(arrays[key]) + 1)
+                    continue
+                _, layer, rest = key.split("/", 2)
+                params[names[rest] + layer[len("layer"):]] = arrays[key]
+        self.engine.load_params(params)

@@ -1,0 +1,319 @@
+"""Training environment with the reference's Trainer API (reference: neuralNetworks/trainer.py).
+
+`Trainer.__init__` used to build a TF graph and every method was a `Session.run`; here the constructor
+creates the CUDA engine and the methods are C-ABI calls:
+
+    update_gradients_op.run(feed)                 -> tfk_accumulate        (trainer.py:165-169, 328)
+    run([average_loss, apply_gradients_op]) + the three re-initialisers
+                                                   -> tfk_apply             (trainer.py:174-184, 337-352)
+    update_valid_loss.run(feed) / average_loss.eval() -> tfk_eval_accumulate / tfk_eval_finish
+    halve_learningrate_op.run()                   -> tfk_halve_lr          (trainer.py:141-142)
+    control_ops['add'] / ['init']                 -> tfk_set_active_layers / output-layer reset
+
+Host batching keeps the reference's micro-batch structure (numutterances_per_minibatch utterances per
+accumulate call) but packs the frames utterance-major into pinned memory instead of padding every
+utterance to max_input_length (trainer.py:276-307) — the in-graph seq2nonseq stripped that padding
+again anyway (classifiers/seq_convertors.py:12-39).
+"""
+from abc import ABCMeta, abstractmethod
+import json
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..engine import Engine
+
+
+class _Op(object):
+    """stand-in for a tf.Operation: something with .run()"""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def run(self):
+        self._fn()
+
+
+class _Stager(object):
+    """Double-buffered pinned staging + side-stream H2D so packing batch k+1 overlaps computing batch k."""
+
+    def __init__(self, device, input_dim, capacity):
+        self.device, self.input_dim, self.capacity = device, input_dim, capacity
+        self.host_x = [torch.empty((capacity, input_dim), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self.host_y = [torch.empty((capacity,), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        self.dev_x = [torch.empty((capacity, input_dim), dtype=torch.float32, device=device) for _ in range(2)]
+        self.dev_y = [torch.empty((capacity,), dtype=torch.int32, device=device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.turn = 0
+        self.used = [False, False]
+
+    def stage(self, mats, targets):
+        """pack utterances (list of [T,I] / [T]) or one packed pair into the next buffer; returns device views"""
+        k = self.turn
+        self.turn ^= 1
+        if self.used[k]:
+            self.copied[k].synchronize()  # the previous H2D out of this pinned buffer has finished
+        hx, hy = self.host_x[k].numpy(), self.host_y[k].numpy()
+        if isinstance(mats, (list, tuple)):
+            n = sum(m.shape[0] for m in mats)
+            if n > self.capacity:
+                raise ValueError("micro-batch of %d frames exceeds the staging capacity %d" % (n, self.capacity))
+            np.concatenate(mats, axis=0, out=hx[:n])
+            off = 0
+            for t in targets:
+                hy[off:off + t.shape[0]] = t  # uint32 -> int32 (placeholder dtype, trainer.py:52-55)
+                off += t.shape[0]
+            if off != n:
+                raise ValueError("inputs hold %d frames but targets %d (CrossEnthropyTrainer needs equal lengths)" % (n, off))
+        else:
+            n = mats.shape[0]
+            if n > self.capacity:
+                raise ValueError("micro-batch of %d frames exceeds the staging capacity %d" % (n, self.capacity))
+            hx[:n] = mats
+            hy[:n] = targets
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.used[k]:
+                self.copy_stream.wait_event(self.consumed[k])  # compute no longer reads this device buffer
+            self.dev_x[k][:n].copy_(self.host_x[k][:n], non_blocking=True)
+            self.dev_y[k][:n].copy_(self.host_y[k][:n], non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        compute.wait_event(self.copied[k])
+        self.used[k] = True
+        return k, self.dev_x[k][:n], self.dev_y[k][:n]
+
+    def release(self, k):
+        self.consumed[k].record(torch.cuda.current_stream(self.device))
+
+
+class Trainer(object, metaclass=ABCMeta):
+    """General training environment for a classifier (trainer.py:9-486)."""
+
+    def __init__(self, classifier, input_dim, max_input_length, max_target_length, init_learning_rate,
+                 learning_rate_decay, num_steps, numutterances_per_minibatch, *, precision="bf16", device=None,
+                 seed=0, max_frames=None, distributed=False):
+        self.classifier = classifier
+        self.input_dim = input_dim
+        self.numutterances_per_minibatch = numutterances_per_minibatch
+        self.max_input_length = max_input_length
+        self.max_target_length = max_target_length
+        self.init_learning_rate = float(init_learning_rate)
+        self.learning_rate_decay = float(learning_rate_decay)
+        self.num_steps = int(num_steps)
+        self.seed = seed
+        spec = classifier.engine_spec(input_dim)
+        self.loss_name = self.compute_loss()
+        if max_frames is None:
+            max_frames = int(numutterances_per_minibatch) * int(max_input_length)
+        self.max_frames = int(max_frames)
+        self.engine = Engine(spec["num_layers"], spec["input_dim"], spec["hidden_dim"], spec["output_dim"], self.max_frames,
+                             nonlin=spec["nonlin"], batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"],
+                             precision=precision, device=device, seed=seed)
+        if distributed:
+            self.engine.init_comm_from_torch()
+        self._stager = None
+        self.summarywriter = None
+        # control operations for layer-by-layer initialisation (classifiers/dnn.py:81-120)
+        if getattr(classifier, "layerwise_init", False):
+            self.engine.set_active_layers(1)  # initialisedlayers = 0 -> logits from activations[0]
+            self.control_ops = {"add": _Op(self._add_layer), "init": _Op(self._init_last_layer)}
+        else:
+            self.control_ops = None
+
+    # ------------------------------------------------------------------ hooks
+    @abstractmethod
+    def compute_loss(self):
+        """name of the loss kernel this trainer minimises (the reference builds the loss graph here,
+        trainer.py:217-242)"""
+        raise NotImplementedError("Abstract method")
+
+    # ------------------------------------------------------------------ graph-level operations
+    def initialize(self):
+        """== init_op.run(): draw the initial parameters (classifiers/layer.py:39-48), zero everything else"""
+        rng = np.random.default_rng(self.seed)
+        self.engine.load_params(self.classifier.initial_parameters(self.input_dim, rng))
+        zero = {"W": (L.T_ADAM_M_W, L.T_ADAM_V_W), "b": (L.T_ADAM_M_B, L.T_ADAM_V_B)}
+        for l in range(self.engine.num_layers + 1):
+            k, n = self.engine.layer_shape(l)
+            for kind in zero["W"]:
+                self.engine.set_tensor(kind, l, np.zeros((k, n), np.float32))
+            for kind in zero["b"]:
+                self.engine.set_tensor(kind, l, np.zeros(n, np.float32))
+            if self.engine.batch_norm and l < self.engine.num_layers:
+                for kind in (L.T_ADAM_M_BETA, L.T_ADAM_V_BETA):
+                    self.engine.set_tensor(kind, l, np.zeros(n, np.float32))
+        self.engine.set_scalar(L.S_GLOBAL_STEP, 0)
+        self.engine.set_scalar(L.S_LR_FACT, 1.0)
+
+    def _add_layer(self):
+        active = int(self.engine.get_scalar(L.S_ACTIVE_LAYERS))
+        self.engine.set_active_layers(min(active + 1, self.engine.num_layers))
+
+    def _init_last_layer(self):
+        """tf.initialize_variables(<output layer scope>) (dnn.py:114-118): weights back to 0, biases to 0;
+        the Adam slots are not part of that collection and keep their values."""
+        l = self.engine.num_layers
+        k, n = self.engine.layer_shape(l)
+        self.engine.set_tensor(L.T_WEIGHTS, l, np.zeros((k, n), np.float32))
+        self.engine.set_tensor(L.T_BIASES, l, np.zeros(n, np.float32))
+
+    def start_visualization(self, logdir):
+        """the reference opens a tf.train.SummaryWriter (trainer.py:249-258); we log the loss as JSON lines"""
+        os.makedirs(logdir, exist_ok=True)
+        self.summarywriter = open(os.path.join(logdir, "loss.jsonl"), "a")
+
+    # ------------------------------------------------------------------ learning rate
+    @property
+    def global_step(self):
+        return int(self.engine.get_scalar(L.S_GLOBAL_STEP))
+
+    def learning_rate(self):
+        """tf.train.exponential_decay(lr0, global_step, num_steps, decay), non-staircase (trainer.py:110-112);
+        the learning_rate_fact factor is applied inside the engine"""
+        return self.init_learning_rate * self.learning_rate_decay ** (float(self.global_step) / float(self.num_steps))
+
+    # ------------------------------------------------------------------ batching
+    def _stage(self, mats, targets):
+        if self._stager is None:
+            self._stager = _Stager(self.engine.device, self.input_dim, self.max_frames)
+        return self._stager.stage(mats, targets)
+
+    def _microbatches(self, inputs, targets):
+        n = self.numutterances_per_minibatch
+        if len(inputs) != len(targets):
+            raise ValueError("inputs and targets hold a different number of utterances")
+        if len(inputs) % n != 0:
+            # the reference pads with (len % n) dummy utterances, which only yields whole micro-batches
+            # when the remainder is 0 (trainer.py:280-294)
+            raise ValueError("the number of utterances (%d) must be a multiple of numutterances_per_minibatch (%d)" % (len(inputs), n))
+        for k in range(len(inputs) // n):
+            yield inputs[k * n:(k + 1) * n], targets[k * n:(k + 1) * n]
+
+    def update(self, inputs, targets):
+        """update the model with a batch: list of [T_u, I] matrices + list of [T_u] target vectors;
+        returns the mean loss per frame evaluated before the update (trainer.py:260-354)"""
+        for mats, tgts in self._microbatches(inputs, targets):
+            k, x, y = self._stage(mats, tgts)
+            self.engine.accumulate(x, y)
+            self._stager.release(k)
+        return self._apply()
+
+    def update_packed(self, x, y, want_loss=True):
+        """fast path: one micro-batch already packed as x [B, I] float32 / y [B] int (pinned host tensors,
+        numpy arrays or device tensors); same arithmetic as update()"""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            self.engine.accumulate(x, y)
+        else:
+            if isinstance(x, torch.Tensor):
+                x, y = x.numpy(), y.numpy()
+            k, dx, dy = self._stage(x, y)
+            self.engine.accumulate(dx, dy)
+            self._stager.release(k)
+        return self._apply(want_loss)
+
+    def _apply(self, want_loss=True):
+        step = self.global_step if self.summarywriter is not None else None
+        loss = self.engine.apply(self.learning_rate_cached(), want_loss)
+        if self.summarywriter is not None and loss is not None:
+            self.summarywriter.write(json.dumps({"step": step, "loss": loss}) + "\n")
+            self.summarywriter.flush()
+        return loss
+
+    def learning_rate_cached(self):
+        if self.learning_rate_decay == 1.0:
+            return self.init_learning_rate
+        return self.learning_rate()
+
+    def evaluate(self, inputs, targets):
+        """mean loss per frame of the eval tower (moving-stat BN, no dropout) (trainer.py:356-441)"""
+        if inputs is None or targets is None:
+            return None
+        for mats, tgts in self._microbatches(inputs, targets):
+            k, x, y = self._stage(mats, tgts)
+            self.engine.eval_accumulate(x, y)
+            self._stager.release(k)
+        return self.engine.eval_finish()
+
+    def halve_learning_rate(self):
+        self.engine.halve_lr()
+
+    # ------------------------------------------------------------------ checkpoints
+    # One .npz per reference checkpoint file, keyed by the reference's TF variable names.
+    def _model_arrays(self):
+        out = {}
+        for key, val in self.engine.dump_params().items():
+            stem = key.rstrip("0123456789")
+            layer = key[len(stem):]
+            name = {"W": "parameters/weights", "b": "parameters/biases", "beta": "activation/batch_norm/beta",
+                    "moving_mean": "activation/batch_norm/moving_mean", "moving_var": "activation/batch_norm/moving_variance"}[stem]
+            out["Classifier/layer%s/%s" % (layer, name)] = val
+        if self.control_ops is not None:
+            out["Classifier/initialisedlayers"] = np.array(int(self.engine.get_scalar(L.S_ACTIVE_LAYERS)) - 1, np.int32)
+        return out
+
+    def _load_model_arrays(self, arrays):
+        names = {"parameters/weights": "W", "parameters/biases": "b", "activation/batch_norm/beta": "beta",
+                 "activation/batch_norm/moving_mean": "moving_mean", "activation/batch_norm/moving_variance": "moving_var"}
+        params = {}
+        for key in arrays.files:
+            if key == "Classifier/initialisedlayers":
+                self.engine.set_active_layers(int(arrays[key]) + 1)
+                continue
+            _, layer, rest = key.split("/", 2)
+            params[names[rest] + layer[len("layer"):]] = arrays[key]
+        self.engine.load_params(params)
+
+    @staticmethod
+    def _path(filename):
+        return filename if filename.endswith(".npz") else filename + ".npz"
+
+    def save_model(self, filename):
+        np.savez(self._path(filename), **self._model_arrays())
+
+    def restore_model(self, filename):
+        with np.load(self._path(filename)) as arrays:
+            self._load_model_arrays(arrays)
+
+    def save_trainer(self, filename):
+        """model + `train_variables` (global_step, learning_rate_fact) (trainer.py:465-475).  The Adam
+        slots are written too (a superset: the reference never checkpoints them)."""
+        self.save_model(filename)
+        np.savez(self._path(filename + "_trainvars"), **{
+            "train_variables/global_step": np.array(self.global_step, np.int32),
+            "train_variables/learning_rate_fact": np.array(self.engine.get_scalar(L.S_LR_FACT), np.float32)})
+        slots = {}
+        for l in range(self.engine.num_layers + 1):
+            slots["W%d/Adam" % l] = self.engine.get_tensor(L.T_ADAM_M_W, l)
+            slots["W%d/Adam_1" % l] = self.engine.get_tensor(L.T_ADAM_V_W, l)
+            slots["b%d/Adam" % l] = self.engine.get_tensor(L.T_ADAM_M_B, l)
+            slots["b%d/Adam_1" % l] = self.engine.get_tensor(L.T_ADAM_V_B, l)
+            if self.engine.batch_norm and l < self.engine.num_layers:
+                slots["beta%d/Adam" % l] = self.engine.get_tensor(L.T_ADAM_M_BETA, l)
+                slots["beta%d/Adam_1" % l] = self.engine.get_tensor(L.T_ADAM_V_BETA, l)
+        np.savez(self._path(filename + "_optimizer"), **slots)
+
+    def restore_trainer(self, filename, restore_optimizer=False):
+        """model + train_variables.  As in the reference the live Adam moments are left untouched
+        (validation rollback keeps them, nnet.py:184-187) unless restore_optimizer=True."""
+        self.restore_model(filename)
+        with np.load(self._path(filename + "_trainvars")) as tv:
+            self.engine.set_scalar(L.S_GLOBAL_STEP, int(tv["train_variables/global_step"]))
+            self.engine.set_scalar(L.S_LR_FACT, float(tv["train_variables/learning_rate_fact"]))
+        if restore_optimizer:
+            kinds = {"W": (L.T_ADAM_M_W, L.T_ADAM_V_W), "b": (L.T_ADAM_M_B, L.T_ADAM_V_B), "beta": (L.T_ADAM_M_BETA, L.T_ADAM_V_BETA)}
+            with np.load(self._path(filename + "_optimizer")) as slots:
+                for key in slots.files:
+                    var, slot = key.split("/")
+                    stem = var.rstrip("0123456789")
+                    self.engine.set_tensor(kinds[stem][0 if slot == "Adam" else 1], int(var[len(stem):]), slots[key])
+
+
+class CrossEnthropyTrainer(Trainer):
+    """minimises the summed per-frame softmax cross-entropy against alignment targets (trainer.py:488-531)"""
+
+    def compute_loss(self):
+        return "softmax_cross_entropy_sum"
