@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the tfkaldi hot path (BASELINE.json): training frames/sec of
+CrossEnthropyTrainer.update on the C2 network (440 -> 6x2048 -> 1936 pdf-ids, 8192 frames per GPU,
+bf16 operands / fp32 accumulate + fp32 master weights, Adam), data-parallel over N GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4] [--precision bf16|bf16x3]
+
+One "step" = one full optimizer step: forward (training mode), summed softmax-CE, backward, gradient
+all-reduce over ranks, mean -> clip -> Adam (reference: neuralNetworks/trainer.py:260-354).
+`--impl reference` times the reference's own CPU implementation of the same step: the reference is
+Python-2 / TensorFlow-0.1x and cannot run here, so it is the CPU restatement in
+oracle/ (fp32, torch-CPU GEMMs on every host core) — the one other place allowed to execute oracle/.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1] / [2]: 6x2048 DNN, 440-in, 1936 tri pdf-ids, batch 8192 per GPU
+    "c2": dict(num_layers=6, input_dim=440, hidden_dim=2048, output_dim=1936, frames=8192, batch_norm=False, keep_prob=1.0),
+    # BASELINE.json configs[3]: + Batchnorm + Dropout 0.5, 3401 lda_mllt pdf-ids, batch 4096
+    "c4": dict(num_layers=6, input_dim=440, hidden_dim=2048, output_dim=3401, frames=4096, batch_norm=True, keep_prob=0.5),
+}
+
+
+def flops_per_frame(c):
+    """3*2*sum(K_l*N_l) - 2*I*H (fwd + dgrad + wgrad, no dgrad for layer 0)"""
+    dims = [c["input_dim"]] + [c["hidden_dim"]] * c["num_layers"] + [c["output_dim"]]
+    fwd = 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    return 3 * fwd - 2 * c["input_dim"] * c["hidden_dim"], fwd
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops_sustained": p.get("bf16_tflops_sustained"), "tflops_burst": p.get("bf16_tflops"), "hbm_gbs": p.get("hbm_gbs"), "source": "measured"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.lines, self.proc, self.idx = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_trainer(c, precision, distributed, seed=1234):
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+
+    chain = act.Batchnorm(None) if c["batch_norm"] else None
+    chain = act.TfActivation(chain, act.relu)
+    if c["keep_prob"] < 1:
+        chain = act.Dropout(chain, c["keep_prob"])
+    dnn = DNN(c["output_dim"], c["num_layers"], c["hidden_dim"], chain, False)
+    tr = CrossEnthropyTrainer(dnn, c["input_dim"], c["frames"], c["frames"], 1e-3, 1.0, 1000000, 1,
+                              precision=precision, seed=seed, max_frames=c["frames"], distributed=distributed)
+    tr.initialize()
+    # output layer N(0, 1/sqrt(H)) for timing so the softmax is non-degenerate
+    rng = np.random.default_rng(seed + 1)
+    from tfkaldi_b200 import _lib as L
+
+    tr.engine.set_tensor(L.T_WEIGHTS, c["num_layers"], (rng.standard_normal((c["hidden_dim"], c["output_dim"])) / math.sqrt(c["hidden_dim"])).astype(np.float32))
+    return tr
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = CONFIGS[args.config]
+    B, I, O = c["frames"], c["input_dim"], c["output_dim"]
+    tr = make_trainer(c, args.precision, world > 1)
+    eng = tr.engine
+    # synthetic data of the reference's shape: post-CMVN spliced frames ~ N(0,1), uniform pdf labels;
+    # a pool of distinct batches, per-rank data seed, identical weights on every rank
+    pool = 4
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_x = [torch.randn((B, I), generator=g, dtype=torch.float32).pin_memory() for _ in range(pool)]
+    host_y = [torch.randint(0, O, (B,), generator=g, dtype=torch.int32).pin_memory() for _ in range(pool)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+    lr = 1e-3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (`value`): inputs already in HBM
+    def step_resident(i):
+        eng.accumulate(dev_x[i % pool], dev_y[i % pool])
+        eng.apply(lr, want_loss=False)  # loss is copied to pinned memory asynchronously, read after the loop
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    ms_resident = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = (eng.kernel_launches() - launches0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end to end (`e2e`): host buffers in, loss out, through the Trainer API
+    for i in range(max(3, args.warmup // 2)):
+        tr.update_packed(host_x[i % pool], host_y[i % pool])
+    barrier()
+    e0.record()
+    last_loss = None
+    tr.prefetch(host_x[0], host_y[0])
+    for i in range(args.steps):
+        # update_packed = wait for this batch's H2D, full step, loss D2H + host sync.  The NEXT batch's
+        # H2D is queued on the copy stream behind this step's kernels' inputs so it overlaps the step
+        # (north_star: "overlapped with the next batch's H2D copy").
+        nxt = (host_x[(i + 1) % pool], host_y[(i + 1) % pool]) if i + 1 < args.steps else None
+        last_loss = tr.update_packed(host_x[i % pool], host_y[i % pool], prefetch=nxt)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    # ---------------- per-kernel CUDA-event timing over the same steps (roofline numerator)
+    eng.enable_timers(True)
+    for i in range(args.steps):
+        step_resident(i)
+    timers = eng.timers()
+    eng.enable_timers(False)
+    train_fl, fwd_fl = flops_per_frame(c)
+    gemm_ms = (timers["gemm_fwd"][0] + timers["gemm_bwd"][0]) / args.steps
+    gemm_launches = (timers["gemm_fwd"][1] + timers["gemm_bwd"][1]) // args.steps
+    peaks = measured_peaks()
+    achieved = train_fl * B / (gemm_ms * 1e-3) / 1e12
+    breakdown = {k: round(v[0] / args.steps * 1e3, 1) for k, v in timers.items() if v[1]}  # us per step
+
+    out = None
+    if rank == 0:
+        frames_total = B * world
+        out = {
+            "metric": "training frames/sec (spliced-fbank->pdf CE), full optimizer step",
+            "value": frames_total / (ms_resident * 1e-3),
+            "unit": "frames/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_resident,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-equivalent)",
+            "data": "synthetic",
+            "config": {"workload": "C2: 440-6x2048-1936 DNN, ReLU, softmax-CE, Adam, %d frames/GPU/step" % B if args.config == "c2"
+                       else "C4: 440-6x2048-3401 DNN, BN+ReLU+dropout(keep 0.5), %d frames/GPU/step" % B,
+                       "frames_per_gpu": B, "global_frames": frames_total, "parallelism": "dp%d" % world, "precision": args.precision,
+                       "l2": "per-step working set (weights+Adam state+grads+activations ~0.9 GB) exceeds the 126 MB L2; %d rotating input batches; no explicit flush" % pool},
+            "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": B * I * 4 + B * 4, "d2h_bytes_per_step": 16,
+                    "api": "CrossEnthropyTrainer.update_packed(pinned x, pinned labels) -> loss", "last_loss": last_loss},
+            "gpu_launches": int(launches * args.steps),
+            "gpu_launches_per_step": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "tfk_gemm_kernel (fused FFLayer fwd + fused wgrad/dgrad, %d launches/step)" % gemm_launches,
+                         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
+                         "peak_source": peaks["source"] + " (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
+                         "algorithmic_flops_per_step": train_fl * B, "kernel_ms_per_step": gemm_ms, "traffic": None,
+                         "step_share": gemm_ms / ms_resident, "per_step_us_by_kernel_class": breakdown},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(c, steps=2)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+_THREADS = {}
+
+
+def _best_thread_count(c):
+    """the baseline gets the thread count that serves it best on this host (more is not always faster
+    on many-core boxes): probe a few settings on one hidden-layer-sized GEMM pair and keep the fastest"""
+    import torch
+
+    key = os.cpu_count()
+    if key in _THREADS:
+        return _THREADS[key]
+    n = os.cpu_count() or 1
+    cands = sorted({n, max(1, n // 2), min(n, 64), min(n, 32), min(n, 16)}, reverse=True)
+    a = torch.randn(4096, c["hidden_dim"])
+    w = torch.randn(c["hidden_dim"], c["hidden_dim"])
+    best, best_t = n, float("inf")
+    for t in cands:
+        torch.set_num_threads(t)
+        torch.mm(a, w)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.mm(a, w)
+            torch.mm(a.t(), a)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = t, dt
+    _THREADS[key] = best
+    return best
+
+
+def cpu_baseline(c, steps, frames=None, warmup=1):
+    """the oracle restatement of the same step on the host cores (reported, not optimised against)"""
+    import torch
+
+    from oracle.dnn_oracle import OracleConfig, OracleDNN, reference_init, set_matmul_backend
+
+    set_matmul_backend("torch")
+    frames = frames or c["frames"]
+    threads = _best_thread_count(c)
+    torch.set_num_threads(threads)
+    cfg = OracleConfig(c["num_layers"], c["input_dim"], c["hidden_dim"], c["output_dim"], batch_norm=c["batch_norm"], keep_prob=c["keep_prob"])
+    rng = np.random.default_rng(1234)
+    params = reference_init(cfg, rng)
+    params["W%d" % c["num_layers"]] = (rng.standard_normal((c["hidden_dim"], c["output_dim"])) / math.sqrt(c["hidden_dim"])).astype(np.float32)
+    orc = OracleDNN(cfg, params)
+    x = rng.standard_normal((frames, c["input_dim"])).astype(np.float32)
+    y = rng.integers(0, c["output_dim"], frames)
+    for _ in range(warmup):
+        orc.accumulate(x, y, dropout_seed=1)
+        orc.apply(1e-3)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        orc.accumulate(x, y, dropout_seed=s)
+        orc.apply(1e-3)
+    dt = time.perf_counter() - t0
+    return {"value": frames * steps / dt, "unit": "frames/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": "%d full optimizer steps of %d frames after %d warm-up (CPU restatement of the reference path; TensorFlow 0.1x cannot run here)" % (steps, frames, warmup),
+            "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation (oracle port), rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    c = CONFIGS[args.config]
+    # bound the run to ~2 minutes whatever K is: the first (warm-up) steps measure the per-step cost
+    frames = c["frames"]
+    budget_s = 120.0
+    probe = cpu_baseline(c, steps=1, frames=frames, warmup=1)
+    per_step = probe["seconds"]
+    total_steps = args.steps + args.warmup
+    if per_step * total_steps > budget_s:
+        frames = max(256, int(frames * budget_s / (per_step * total_steps)) // 256 * 256)
+    res = cpu_baseline(c, steps=args.steps, frames=frames, warmup=min(args.warmup, 3) if frames == c["frames"] else args.warmup)
+    train_fl, _ = flops_per_frame(c)
+    out = {
+        "impl": "reference",
+        "metric": "training frames/sec (spliced-fbank->pdf CE), full optimizer step",
+        "value": res["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["seconds"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: 440-6x2048-1936 DNN, ReLU, softmax-CE, Adam" if args.config == "c2" else "C4", "frames_per_step": frames,
+                   "note": "reference = vrenkens/tfkaldi CrossEnthropyTrainer.update semantics restated on CPU (oracle/dnn_oracle.py); the TF-0.1x/Python-2 original cannot execute in this image"},
+        "cpu_baseline": {"value": res["value"], "unit": "frames/s", "cores": res["cores"], "kind": "port",
+                         "sample": "%d steps of %d frames each (of the %d-frame workload)" % (args.steps, frames, c["frames"])},
+        "e2e": {"value": res["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "achieved_tflops": train_fl * res["value"] / 1e12,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,7 +40,8 @@ def _mm(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     if _MATMUL_BACKEND == "torch":
         import torch
 
-        return torch.mm(torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b))).numpy()
+        # from_numpy keeps transposed views as strides: MKL takes them as transposition flags, no copy
+        return torch.mm(torch.from_numpy(a), torch.from_numpy(b)).numpy()
     return np.matmul(a, b)
 
 
@@ -72,7 +73,7 @@ def reference_init(cfg: OracleConfig, rng: np.random.Generator) -> dict:
         k = cfg.input_dim if l == 0 else cfg.hidden_dim
         n = cfg.hidden_dim if l < cfg.num_layers else cfg.output_dim
         if l < cfg.num_layers:
-            p[f"W{l}"] = (rng.standard_normal((k, n)) / math.sqrt(k)).astype(F32)
+            p[f"W{l}"] = (rng.standard_normal((k, n)) / math.sqrt(k)).astype(F32, copy=False)
         else:
             p[f"W{l}"] = np.zeros((k, n), F32)
         p[f"b{l}"] = np.zeros(n, F32)
@@ -135,16 +136,16 @@ class OracleDNN:
                 c.z = z
                 if training:
                     # tf.nn.moments over the micro-batch: biased variance (App. A.3)
-                    mu = z.mean(axis=0, dtype=np.float64).astype(F32)
-                    var = np.mean(np.square(z - mu, dtype=np.float64), axis=0).astype(F32)
+                    mu = z.mean(axis=0, dtype=np.float64).astype(F32, copy=False)
+                    var = np.mean(np.square(z - mu, dtype=np.float64), axis=0).astype(F32, copy=False)
                     # assign_moving_average, run through UPDATE_OPS once per micro-batch (trainer.py:164-168)
                     d = F32(1.0 - cfg.bn_decay)
                     self.p[f"moving_mean{l}"] -= d * (self.p[f"moving_mean{l}"] - mu)
                     self.p[f"moving_var{l}"] -= d * (self.p[f"moving_var{l}"] - var)
                 else:
                     mu, var = self.p[f"moving_mean{l}"], self.p[f"moving_var{l}"]
-                c.rstd = (F32(1.0) / np.sqrt(var + F32(cfg.bn_eps))).astype(F32)
-                c.xhat = ((z - mu) * c.rstd).astype(F32)
+                c.rstd = (F32(1.0) / np.sqrt(var + F32(cfg.bn_eps))).astype(F32, copy=False)
+                c.xhat = ((z - mu) * c.rstd).astype(F32, copy=False)
                 h = c.xhat + self.p[f"beta{l}"]  # center=True, scale=False
             else:
                 h = z
@@ -152,12 +153,12 @@ class OracleDNN:
             if training and cfg.keep_prob < 1.0:
                 # tf.nn.dropout: x / keep * floor(keep + u)   classifiers/activation.py:140-141
                 keep = dropout_keep_mask(dropout_seed + l, h.shape[0], h.shape[1], cfg.keep_prob)
-                h = np.where(keep, h * F32(1.0 / cfg.keep_prob), F32(0)).astype(F32)
-            c.y = h.astype(F32)
+                h = np.where(keep, h * F32(1.0 / cfg.keep_prob), F32(0)).astype(F32, copy=False)
+            c.y = h.astype(F32, copy=False)
             caches.append(c)
             a = c.y
         cl = _LayerCache(x=a)
-        logits = (_mm(a, self.p[f"W{self.L}"]) + self.p[f"b{self.L}"]).astype(F32)
+        logits = (_mm(a, self.p[f"W{self.L}"]) + self.p[f"b{self.L}"]).astype(F32, copy=False)
         caches.append(cl)
         return logits, caches
 
@@ -168,7 +169,7 @@ class OracleDNN:
         softmax_cross_entropy_with_logits(logits, one_hot(labels)); returns (loss_sum, dlogits)
         with dlogits = softmax - onehot (not divided by the frame count).
         Labels outside [0,O) give an all-zero one-hot row (tf.one_hot) => loss 0, gradient 0."""
-        z = logits.astype(F32)
+        z = logits.astype(F32, copy=False)
         mx = z.max(axis=1, keepdims=True)
         e = np.exp(z - mx)
         s = e.sum(axis=1, keepdims=True, dtype=F32)
@@ -176,12 +177,12 @@ class OracleDNN:
         ok = (labels >= 0) & (labels < z.shape[1])
         idx = np.where(ok, labels, 0)
         rows = np.arange(z.shape[0])
-        row_loss = (np.log(s[:, 0]) + mx[:, 0] - z[rows, idx]).astype(F32)
+        row_loss = (np.log(s[:, 0]) + mx[:, 0] - z[rows, idx]).astype(F32, copy=False)
         row_loss = np.where(ok, row_loss, F32(0))
-        d = (e / s).astype(F32)
+        d = (e / s).astype(F32, copy=False)
         d[rows, idx] -= F32(1)
         d[~ok] = 0
-        return float(row_loss.sum(dtype=np.float64)), d.astype(F32)
+        return float(row_loss.sum(dtype=np.float64)), d.astype(F32, copy=False)
 
     # ------------------------------------------------------------------ backward
     def backward(self, caches, dlogits: np.ndarray) -> dict:
@@ -190,9 +191,9 @@ class OracleDNN:
         g = {}
         L = self.L
         cl = caches[-1]
-        g[f"W{L}"] = _mm(cl.x.T, dlogits).astype(F32)
+        g[f"W{L}"] = _mm(cl.x.T, dlogits).astype(F32, copy=False)
         g[f"b{L}"] = dlogits.sum(axis=0, dtype=F32)
-        da = _mm(dlogits, self.p[f"W{L}"].T).astype(F32)
+        da = _mm(dlogits, self.p[f"W{L}"].T).astype(F32, copy=False)
         for l in range(self.active - 1, -1, -1):
             c = caches[l]
             # dropout + nonlinearity backward.  With y = nonlin(h)/keep*mask: relu passes where y > 0
@@ -203,20 +204,23 @@ class OracleDNN:
                 passed = c.y != 0
             else:
                 passed = None
-            scale = F32(1.0 / cfg.keep_prob) if cfg.keep_prob < 1.0 else F32(1)
-            dh = da * scale if passed is None else np.where(passed, da * scale, F32(0)).astype(F32)
+            dh = da
+            if cfg.keep_prob < 1.0:
+                dh = dh * F32(1.0 / cfg.keep_prob)
+            if passed is not None:
+                dh = np.multiply(dh, passed, dtype=F32)  # zero where the unit did not pass
             if cfg.batch_norm:
                 # y = xhat + beta: dbeta = sum dy; dz = r * (dy - mean(dy) - xhat * mean(dy*xhat))  (App. A.3)
                 g[f"beta{l}"] = dh.sum(axis=0, dtype=F32)
-                m1 = dh.mean(axis=0, dtype=np.float64).astype(F32)
-                m2 = (dh * c.xhat).mean(axis=0, dtype=np.float64).astype(F32)
-                dz = (c.rstd * (dh - m1 - c.xhat * m2)).astype(F32)
+                m1 = dh.mean(axis=0, dtype=np.float64).astype(F32, copy=False)
+                m2 = (dh * c.xhat).mean(axis=0, dtype=np.float64).astype(F32, copy=False)
+                dz = (c.rstd * (dh - m1 - c.xhat * m2)).astype(F32, copy=False)
             else:
                 dz = dh
-            g[f"W{l}"] = _mm(c.x.T, dz).astype(F32)
+            g[f"W{l}"] = _mm(c.x.T, dz).astype(F32, copy=False)
             g[f"b{l}"] = dz.sum(axis=0, dtype=F32)
             if l > 0:
-                da = _mm(dz, self.p[f"W{l}"].T).astype(F32)
+                da = _mm(dz, self.p[f"W{l}"].T).astype(F32, copy=False)
         return g
 
     # ------------------------------------------------------------------ trainer steps
@@ -247,7 +251,19 @@ class OracleDNN:
         lr_t = F32(lr * self.lr_fact * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
         nf = F32(self.num_frames)
         for k in self.trainable:
-            ghat = np.clip(self.grads[k] / nf, F32(-1), F32(1)).astype(F32)
+            if _MATMUL_BACKEND == "torch":
+                # same fp32 formulas through torch's multi-threaded element-wise kernels (in place on
+                # the numpy buffers) so the timed CPU baseline uses every host core, as TF-CPU's Eigen would
+                import torch
+
+                g, m, v, w = (torch.from_numpy(a) for a in (self.grads[k], self.m[k], self.v[k], self.p[k]))
+                ghat = torch.clamp(g / float(nf), -1.0, 1.0)
+                m.add_((ghat - m) * float(F32(1.0 - b1)))
+                v.add_((ghat * ghat - v) * float(F32(1.0 - b2)))
+                w.sub_((m * float(lr_t)) / (torch.sqrt(v) + float(F32(cfg.adam_eps))))
+                g.zero_()
+                continue
+            ghat = np.clip(self.grads[k] / nf, F32(-1), F32(1)).astype(F32, copy=False)
             self.m[k] += (ghat - self.m[k]) * F32(1.0 - b1)
             self.v[k] += (ghat * ghat - self.v[k]) * F32(1.0 - b2)
             self.p[k] -= (self.m[k] * lr_t) / (np.sqrt(self.v[k]) + F32(cfg.adam_eps))
@@ -278,13 +294,13 @@ class OracleDNN:
         logits, _ = self.forward(x, training=False)
         mx = logits.max(axis=1, keepdims=True)
         e = np.exp(logits - mx)
-        return (e / e.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
+        return (e / e.sum(axis=1, keepdims=True, dtype=F32)).astype(F32, copy=False)
 
     def loglik(self, x, prior) -> np.ndarray:
         """Nnet.decode post-processing (nnet.py:280-286): log(posterior / prior), float32, NO flooring
         (the reference's np.where result is discarded)."""
         with np.errstate(divide="ignore", invalid="ignore"):
-            return np.log(self.posteriors(x) / np.asarray(prior, dtype=F32)).astype(F32)
+            return np.log(self.posteriors(x) / np.asarray(prior, dtype=F32)).astype(F32, copy=False)
 
 
 def learning_rate(lr0: float, decay: float, global_step: int, num_steps: int) -> float:
@@ -295,5 +311,5 @@ def learning_rate(lr0: float, decay: float, global_step: int, num_steps: int) ->
 def compute_prior(target_arrays, num_labels: int) -> np.ndarray:
     """nnet.py:241-244 + batchdispenser.py:128-145: bincount over ALL targets, float32, normalised."""
     count = np.bincount(np.concatenate([np.asarray(t) for t in target_arrays]), minlength=num_labels)
-    prior = count.astype(F32)
+    prior = count.astype(F32, copy=False)
     return prior / prior.sum()

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -81,8 +82,9 @@ struct Layer {
   __nv_bfloat16 *z_hi = nullptr, *z_lo = nullptr;        // pre-BN linear output [maxB, ldn]
 };
 
-struct Plan {  // TMA descriptors for one (frames, active layers) shape
+struct Plan {  // TMA descriptors (+ CTA-pair work lists) for one (frames, active layers) shape
   std::vector<GemmParams> fwd_train, fwd_eval, bwd;
+  std::vector<int*> lists;  // device work lists owned by the plan
 };
 
 }  // namespace
@@ -92,6 +94,7 @@ struct tfk_handle {
   int L = 0;        // hidden layers
   int active = 0;   // hidden layers in use (layer-wise growth)
   bool x3 = false;
+  bool two_cta = true;  // cta_group::2 CTA-pair GEMM (TFK_GEMM_2CTA=0 selects the 1-CTA kernel)
   int num_sms = 148;
   std::vector<Layer> layers;  // L+1
   size_t arena_n = 0;
@@ -107,6 +110,7 @@ struct tfk_handle {
   double* acc_host = nullptr;
   float *bn_ps = nullptr, *bn_pq = nullptr;
   float* ws = nullptr;
+  float* ws_colsum = nullptr;
   float* tmp_f32 = nullptr;
   int* sched = nullptr;
   std::map<long long, Plan> plans;
@@ -221,9 +225,24 @@ int drain_timers(tfk_handle* h) {
 // ------------------------------------------------------------------ plans
 void base_operands(tfk_handle* h, GemmSpec& s) { s.nsplit = h->x3 ? 3 : 1; }
 
+int finish_params(tfk_handle* h, Plan& plan, const GemmSpec* s, int n, GemmParams* gp, const char* what, int l) {
+  char err[256] = {0};
+  if (gemm_build_params(s, n, h->sched, gp, err, sizeof(err), h->two_cta ? 1 : 0))
+    return fail(h, TFK_ECUDA, "%s plan layer %d: %s", what, l, err);
+  int* d = nullptr;
+  if (gemm_upload_tile_lists(gp, h->num_sms, &d, err, sizeof(err)))
+    return fail(h, TFK_ECUDA, "%s plan layer %d: %s", what, l, err);
+  if (d) plan.lists.push_back(d);
+  return TFK_OK;
+}
+
+void free_plan(Plan& plan) {
+  for (int* d : plan.lists) cudaFree(d);
+  plan.lists.clear();
+}
+
 int build_plan(tfk_handle* h, int B, Plan& plan) {
   const int L = h->L, act = h->active;
-  char err[256] = {0};
   const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU;
   const bool drop = h->cfg.keep_prob < 1.0f;
   plan.fwd_train.assign(L + 1, GemmParams());
@@ -254,8 +273,7 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
         if (train && drop) { s.keep = h->cfg.keep_prob; s.seed = 0; }
       }
       GemmParams& gp = train ? plan.fwd_train[l] : plan.fwd_eval[l];
-      if (gemm_build_params(&s, 1, h->sched, &gp, err, sizeof(err)))
-        return fail(h, TFK_ECUDA, "forward plan layer %d: %s", l, err);
+      TFK_TRY(finish_params(h, plan, &s, 1, &gp, "forward", l));
     }
     // backward: problem 0 = wgrad (long K first), problem 1 = dgrad into the layer below
     const __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
@@ -267,6 +285,20 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
     s[0].A_hi = h->act_hi[ai]; s[0].A_lo = h->act_lo[ai]; s[0].lda = ly.ldk; s[0].a_mn = 1;
     s[0].B_hi = dz_hi; s[0].B_lo = dz_lo; s[0].ldb = ldz; s[0].b_mn = 1;
     s[0].out_kind = OUT_F32_REDADD; s[0].D_hi = h->G + ly.off_w; s[0].ldd = ly.ldn;
+    {
+      // split the frame (reduction) dimension so a wgrad alone can fill the SMs; partials meet in the
+      // TMA reduce-add.  Keep >= 16 k-blocks (1024 frames) per work item.
+      const int tile_m = h->two_cta ? 256 : BM;
+      const int tiles = ((ly.K + tile_m - 1) / tile_m) * ((ly.N + BN - 1) / BN);
+      const int kb = (B + BK - 1) / BK;
+      const int units = h->two_cta ? h->num_sms / 2 : h->num_sms;  // concurrent tiles
+      // only when the launch cannot fill the machine otherwise (layer 0: its wgrad runs alone and has
+      // few output tiles); hidden layers share their launch with 4x more dgrad tiles and measured slower
+      // with split-K (extra reduce-add traffic)
+      int ks = (ai > 0 || tiles >= units) ? 1 : (2 * units + tiles - 1) / tiles;
+      if (ks > kb / 16) ks = kb / 16;
+      s[0].ksplit = ks < 1 ? 1 : ks;
+    }
     int nspec = 1;
     if (ai > 0) {
       // dX[B, K] = dZ[B, N] . W[K, N]^T, masked by the forward output of the layer below
@@ -285,8 +317,7 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       }
       nspec = 2;
     }
-    if (gemm_build_params(s, nspec, h->sched, &plan.bwd[l], err, sizeof(err)))
-      return fail(h, TFK_ECUDA, "backward plan layer %d: %s", l, err);
+    TFK_TRY(finish_params(h, plan, s, nspec, &plan.bwd[l], "backward", l));
   }
   return TFK_OK;
 }
@@ -295,9 +326,16 @@ int get_plan(tfk_handle* h, int B, Plan** out) {
   const long long key = static_cast<long long>(B) * 64 + h->active;
   auto it = h->plans.find(key);
   if (it == h->plans.end()) {
-    if (h->plans.size() > 64) h->plans.clear();
+    if (h->plans.size() > 64) {
+      cudaDeviceSynchronize();
+      for (auto& kv : h->plans) free_plan(kv.second);
+      h->plans.clear();
+    }
     Plan p;
-    TFK_TRY(build_plan(h, B, p));
+    if (int rc = build_plan(h, B, p)) {
+      free_plan(p);
+      return rc;
+    }
     it = h->plans.emplace(key, std::move(p)).first;
   }
   *out = &it->second;
@@ -360,8 +398,8 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
                                  ly.bn_sums, st));
   }
   {
-    TimerScope ts(h, st, TFK_TIMER_COLSUM, 2);
-    TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws, h->G + ly.off_b, st));
+    TimerScope ts(h, st, TFK_TIMER_COLSUM);
+    TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws_colsum, h->G + ly.off_b, st));
   }
   {
     TimerScope ts(h, st, TFK_TIMER_GEMM_BWD);
@@ -507,6 +545,7 @@ int tfk_destroy(tfk_handle* h) {
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  for (auto& kv : h->plans) free_plan(kv.second);
   for (void* p : h->allocs) cudaFree(p);
   if (h->acc_host) cudaFreeHost(h->acc_host);
   delete h;
@@ -542,6 +581,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
   h->active = h->L;
   h->x3 = cfg->precision == TFK_PREC_BF16X3;
   h->drop_seed = cfg->seed;
+  if (const char* e = getenv("TFK_GEMM_2CTA")) h->two_cta = atoi(e) != 0;
   auto bail = [&](int rc) {
     g_create_error = h->err;
     tfk_destroy(h);
@@ -628,7 +668,8 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     CREATE_TRY(dev_alloc(h, &h->bn_ps, n));
     CREATE_TRY(dev_alloc(h, &h->bn_pq, n));
   }
-  CREATE_TRY(dev_alloc(h, &h->ws, 64 * static_cast<size_t>(h->ldmax)));
+  CREATE_TRY(dev_alloc(h, &h->ws, 64 * static_cast<size_t>(h->ldmax)));        // bn backward partials
+  CREATE_TRY(dev_alloc(h, &h->ws_colsum, 1024 + 32 * static_cast<size_t>(h->ldmax)));  // colsum counters + partials
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
   {
@@ -797,10 +838,17 @@ int tfk_fflayer_bwd(tfk_handle* h, int layer, const float* dy, float* dx, int B,
     s[1].D_hi = h->dA_hi[dst]; s[1].D_lo = h->dA_lo[dst]; s[1].ldd = ly.ldk;
   }
   GemmParams gp;
-  char err[256] = {0};
-  if (gemm_build_params(s, dx ? 2 : 1, h->sched, &gp, err, sizeof(err)))
-    return fail(h, TFK_ECUDA, "tfk_fflayer_bwd plan: %s", err);
-  TFK_TRY(backward_layer(h, *plan, B, layer, st, &gp));
+  Plan scratch;
+  if (int rc = finish_params(h, scratch, s, dx ? 2 : 1, &gp, "tfk_fflayer_bwd", layer)) {
+    free_plan(scratch);
+    return rc;
+  }
+  const int brc = backward_layer(h, *plan, B, layer, st, &gp);
+  if (!scratch.lists.empty()) {  // the ad-hoc work list must outlive the launch
+    cudaStreamSynchronize(st);
+    free_plan(scratch);
+  }
+  TFK_TRY(brc);
   if (dx) {
     TimerScope ts(h, st, TFK_TIMER_CONVERT);
     TFK_LAUNCH(h, k_merge_bf16(h->dA_hi[dst], h->dA_lo[dst], ly.ldk, dx, ly.K, B, ly.K, st));

@@ -10,8 +10,10 @@
 // one launch balance across the 148 SMs).
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "philox.cuh"
 #include "ptx.cuh"
@@ -31,6 +33,19 @@ constexpr uint32_t SMEM_USED = BARS_OFF + 256;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-byte alignment
 constexpr uint32_t MN_ATOM_BYTES = 64 * BK * 2;    // one 64(MN) x 64(K) TMA box = 8 KB
 
+// CTA-pair kernel: per CTA a stage holds its 128 A rows and its 128 of the 256 B rows (16 KB each)
+constexpr int STAGES2 = 6;
+constexpr uint32_t STAGE2_BYTES = 2 * A_TILE_BYTES;
+static_assert(STAGES2 * STAGE2_BYTES == SLABS_OFF, "both kernels share one smem carve-up");
+struct SmemBars2 {
+  uint64_t full[STAGES2];
+  uint64_t empty[STAGES2];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SmemBars2) <= 256, "barrier block too large");
+
 struct SmemBars {
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
@@ -45,15 +60,21 @@ static_assert(sizeof(SmemBars) <= 256, "barrier block too large");
 
 struct TileCoord {
   int p, m_blk, n_blk;
+  int kb_begin, kb_count;  // k-block range of this work item (split-K)
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
   TileCoord t;
   t.p = (P.nprob > 1 && tile >= P.p[1].tile_begin) ? 1 : 0;
-  const int local = tile - P.p[t.p].tile_begin;
-  const int tn = P.p[t.p].tiles_n;
-  t.m_blk = local / tn;
-  t.n_blk = local - t.m_blk * tn;
+  const GemmProblem& pr = P.p[t.p];
+  int local = tile - pr.tile_begin;
+  const int per_split = pr.tiles_m * pr.tiles_n;
+  const int split = local / per_split;
+  local -= split * per_split;
+  t.m_blk = local / pr.tiles_n;
+  t.n_blk = local - t.m_blk * pr.tiles_n;
+  t.kb_begin = split * pr.kb_per_split;
+  t.kb_count = min(pr.kb_per_split, pr.num_kb - t.kb_begin);
   return t;
 }
 
@@ -325,8 +346,8 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
         const TileCoord tc = decode_tile(P, tile);
         const GemmProblem& pr = P.p[tc.p];
         const int m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
-        const int iters = pr.num_kb * pr.nsplit;
-        int kb = 0, s = 0;
+        const int iters = tc.kb_count * pr.nsplit;
+        int kb = tc.kb_begin, s = 0;
         for (int i = 0; i < iters; ++i) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
@@ -393,7 +414,7 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
         //           advance 2 K-groups (2048 B) per UMMA_K.
         const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
         const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
-        const int iters = pr.num_kb * pr.nsplit;
+        const int iters = tc.kb_count * pr.nsplit;
         for (int i = 0; i < iters; ++i) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
@@ -473,6 +494,195 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel: two CTAs (one cluster, two SMs of a TPC) own one 256 x 256 tile.  Each CTA stages
+// its own 128 rows of A and 128 of the 256 B rows, so a k-block costs 32 KB of L2->smem traffic per SM
+// instead of 48 KB and 8 KB instead of 12 KB of operand reads per MMA; the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) for both.  Accumulator rows 0-127 live in the leader's TMEM,
+// rows 128-255 in the peer's; each CTA runs the same epilogue on its half.
+// Work distribution is a static, host-computed longest-first list per pair (tile durations are known
+// from their k-extent), read by both CTAs, so no cross-CTA scheduling traffic is needed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  SmemBars2* bars = reinterpret_cast<SmemBars2*>(smem_gen + BARS_OFF);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int* __restrict__ my_list = P.tile_list + static_cast<size_t>(pair) * P.list_stride;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.nprob; ++p) {
+      tma_prefetch_desc(&P.p[p].tmA[0]);
+      tma_prefetch_desc(&P.p[p].tmB[0]);
+      tma_prefetch_desc(&P.p[p].tmD[0]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES2; ++i) {
+        mbar_init(&bars->full[i], 1);   // leader: one arrive.expect_tx; bytes arrive from both CTAs' TMA
+        mbar_init(&bars->empty[i], 1);  // multicast tcgen05.commit from the leader
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->tmem_full[i], 1);   // multicast tcgen05.commit from the leader
+        mbar_init(&bars->tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / TMA signal
+  if (warp == 1) tmem_alloc_2sm(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0;; ++it) {
+        const int tile = __ldg(my_list + it);
+        if (tile < 0) break;
+        const TileCoord tc = decode_tile(P, tile);
+        const GemmProblem& pr = P.p[tc.p];
+        const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128;  // this CTA's A / D rows
+        const int nb = tc.n_blk * BN + static_cast<int>(rank) * 128;   // this CTA's half of the B rows
+        const int iters = tc.kb_count * pr.nsplit;
+        int kb = tc.kb_begin, s = 0;
+        for (int i = 0; i < iters; ++i) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&bars->full[stage], 2 * STAGE2_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const CUtensorMap* ta = &pr.tmA[s == 2 ? 1 : 0];
+          const CUtensorMap* tb = &pr.tmB[s == 1 ? 1 : 0];
+          const int k0 = kb * BK;
+          if (pr.a_mn) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_2sm(sa + j * MN_ATOM_BYTES, ta, &bars->full[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_2sm(sa, ta, &bars->full[stage], k0, m0);
+          }
+          if (pr.b_mn) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_2sm(sb + j * MN_ATOM_BYTES, tb, &bars->full[stage], nb + 64 * j, k0);
+          } else {
+            tma_load_2d_2sm(sb, tb, &bars->full[stage], k0, nb);
+          }
+          if (++s == pr.nsplit) {
+            s = 0;
+            ++kb;
+          }
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ============================
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0;; ++it) {
+        const int tile = __ldg(my_list + it);
+        if (tile < 0) break;
+        const TileCoord tc = decode_tile(P, tile);
+        const GemmProblem& pr = P.p[tc.p];
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait_cluster(&bars->tmem_empty[as], aphase ^ 1);  // both CTAs' epilogues drained this stage
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        const uint32_t idesc = make_idesc_bf16(256, BN, pr.a_mn, pr.b_mn);
+        const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
+        const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
+        const int iters = tc.kb_count * pr.nsplit;
+        for (int i = 0; i < iters; ++i) {
+          mbar_wait_cluster(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
+            const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
+            umma_bf16_2sm(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&bars->empty[stage]);  // frees this smem slot in BOTH CTAs
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&bars->tmem_full[as]);  // accumulator halves ready in both CTAs
+      }
+    }
+  } else {
+    // ============================ epilogue warps (both CTAs, own 128 rows) ============================
+    const uint32_t q = warp & 3;
+    const uint32_t slab_base = smem_base + SLABS_OFF + (warp - 2) * 2 * SLAB_BYTES;
+    int sbuf = 0, prev_split = 0;
+    for (int it = 0;; ++it) {
+      const int tile = __ldg(my_list + it);
+      if (tile < 0) break;
+      const TileCoord tc = decode_tile(P, tile);
+      const GemmProblem& pr = P.p[tc.p];
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait_cluster(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN;
+      const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN;
+      const int is_split = pr.out_kind == OUT_BF16_SPLIT;
+      if (is_split != prev_split) {
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
+        prev_split = is_split;
+        sbuf = 0;
+      }
+      if (m0 < pr.M) {  // a ragged last pair-tile may leave the peer CTA without rows
+        switch (pr.out_kind) {
+          case OUT_BF16:
+            epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+            break;
+          case OUT_BF16_SPLIT:
+            epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+            break;
+          case OUT_F32:
+            epilogue_tile<OUT_F32>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+            break;
+          default:
+            epilogue_tile<OUT_F32_REDADD>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
+            break;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[as]);
+    }
+    if (lane == 0) tma_wait_group<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal / read it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -533,12 +743,14 @@ int gemm_init() {
   cudaError_t e = cudaFuncSetAttribute(tfk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(tfk_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
   done = 1;
   return 0;
 }
 
 int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* out, char* err,
-                      int errlen) {
+                      int errlen, int two_cta) {
   if (nspec < 1 || nspec > 2) {
     snprintf(err, errlen, "gemm_build_params: nspec must be 1 or 2");
     return -1;
@@ -546,6 +758,8 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
   memset(out, 0, sizeof(GemmParams));
   out->nprob = nspec;
   out->sched = sched;
+  out->two_cta = two_cta ? 1 : 0;
+  const uint32_t b_box_rows = two_cta ? 128 : BN;  // a CTA of a pair stages half of the 256 B rows
   int tile_begin = 0;
   for (int i = 0; i < nspec; ++i) {
     const GemmSpec& s = specs[i];
@@ -577,8 +791,8 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
         rc = make_tmap(&p.tmB[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, s.N, s.K, s.ldb, 64, BK, err,
                        errlen);
       else
-        rc = make_tmap(&p.tmB[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, s.K, s.N, s.ldb, BK, BN, err,
-                       errlen);
+        rc = make_tmap(&p.tmB[h], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, s.K, s.N, s.ldb, BK, b_box_rows,
+                       err, errlen);
       if (rc) return rc;
     }
     if (s.out_kind == OUT_F32 || s.out_kind == OUT_F32_REDADD) {
@@ -614,11 +828,21 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.stat_sum = s.stat_sum;
     p.stat_sq = s.stat_sq;
     p.stat_ld = s.stat_ld;
-    p.tiles_m = (s.M + BM - 1) / BM;
+    p.tiles_m = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     p.tiles_n = (s.N + BN - 1) / BN;
     p.tile_begin = tile_begin;
     p.num_kb = (s.K + BK - 1) / BK;
-    tile_begin += p.tiles_m * p.tiles_n;
+    p.ksplit = 1;
+    if (s.ksplit > 1) {
+      if (s.out_kind != OUT_F32_REDADD) {
+        snprintf(err, errlen, "gemm: ksplit needs OUT_F32_REDADD");
+        return -1;
+      }
+      p.ksplit = s.ksplit < p.num_kb ? s.ksplit : p.num_kb;
+    }
+    p.kb_per_split = (p.num_kb + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+    tile_begin += p.tiles_m * p.tiles_n * p.ksplit;
   }
   out->total_tiles = tile_begin;
   return 0;
@@ -627,9 +851,63 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
 int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream) {
   int rc = gemm_init();
   if (rc) return rc;
+  if (params.two_cta) {
+    if (params.tile_list == nullptr || params.num_pairs < 1) return (int)cudaErrorInvalidValue;
+    tfk_gemm2_kernel<<<2 * params.num_pairs, GEMM_THREADS, SMEM_BYTES, stream>>>(params);
+    return (int)cudaGetLastError();
+  }
   const int grid = params.total_tiles < num_sms ? params.total_tiles : num_sms;
   tfk_gemm_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(params);
   return (int)cudaGetLastError();
+}
+
+int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* err, int errlen) {
+  *d_list = nullptr;
+  if (!params->two_cta) return 0;
+  const int total = params->total_tiles;
+  int pairs = num_sms / 2;
+  if (pairs > total) pairs = total;
+  if (pairs < 1) pairs = 1;
+  // cost model: k-extent (MMA time) + a constant for the epilogue, in k-block units
+  std::vector<std::pair<long long, int>> order(total);
+  for (int t = 0; t < total; ++t) {
+    const int pi = (params->nprob > 1 && t >= params->p[1].tile_begin) ? 1 : 0;
+    const GemmProblem& pr = params->p[pi];
+    const int local = t - pr.tile_begin;
+    const int split = local / (pr.tiles_m * pr.tiles_n);
+    const int kb0 = split * pr.kb_per_split;
+    const int cnt = pr.kb_per_split < pr.num_kb - kb0 ? pr.kb_per_split : pr.num_kb - kb0;
+    order[t] = {static_cast<long long>(cnt) * pr.nsplit + 6, t};
+  }
+  std::stable_sort(order.begin(), order.end(),
+                   [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first > b.first; });
+  std::vector<std::vector<int>> lists(pairs);
+  std::vector<long long> load(pairs, 0);
+  for (const auto& it : order) {
+    int best = 0;
+    for (int p = 1; p < pairs; ++p)
+      if (load[p] < load[best]) best = p;
+    lists[best].push_back(it.second);
+    load[best] += it.first;
+  }
+  size_t stride = 1;
+  for (const auto& l : lists) stride = l.size() + 1 > stride ? l.size() + 1 : stride;
+  std::vector<int> flat(static_cast<size_t>(pairs) * stride, -1);
+  for (int p = 0; p < pairs; ++p)
+    for (size_t i = 0; i < lists[p].size(); ++i) flat[p * stride + i] = lists[p][i];
+  int* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, flat.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "tile list upload failed: %s", cudaGetErrorString(e));
+    if (d) cudaFree(d);
+    return -2;
+  }
+  params->num_pairs = pairs;
+  params->list_stride = static_cast<int>(stride);
+  params->tile_list = d;
+  *d_list = d;
+  return 0;
 }
 
 }  // namespace tfk

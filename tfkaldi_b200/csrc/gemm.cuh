@@ -43,6 +43,7 @@ struct GemmSpec {
   int ldb = 0;
   int b_mn = 0;    // 0: B stored [N,K];  1: B stored [K,N]
   int nsplit = 1;  // 1: plain bf16;  3: bf16x3 (Ah.Bh + Ah.Bl + Al.Bh), ~fp32 accuracy
+  int ksplit = 1;  // split the reduction over this many work items (OUT_F32_REDADD only: partials add up)
   int out_kind = OUT_BF16;
   void* D_hi = nullptr;
   void* D_lo = nullptr;
@@ -78,19 +79,28 @@ struct alignas(64) GemmProblem {
   float* stat_sq;
   int stat_ld;
   int tiles_m, tiles_n, tile_begin, num_kb;
+  int ksplit, kb_per_split;
 };
 
 struct alignas(64) GemmParams {
   GemmProblem p[2];
   int nprob;
   int total_tiles;
-  int* sched;  // [2]: {next tile counter, finished-CTA counter}; self-resetting
+  int* sched;  // [2]: {next tile counter, finished-CTA counter}; self-resetting (1-CTA kernel)
+  // CTA-pair kernel (cta_group::2, 256x256 tiles): static longest-first work lists, one per pair
+  int two_cta;
+  int num_pairs;
+  int list_stride;
+  const int* tile_list;  // device [num_pairs, list_stride], -1 terminated
 };
 
 // Build the kernel parameters (tensor maps) for up to two problems.  Long-K problems should come first.
 // Returns 0 on success, negative on error (message in err).
 int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* out, char* err,
-                      int errlen);
+                      int errlen, int two_cta = 0);
+// CTA-pair plans only: compute the per-pair longest-processing-time-first work lists and upload them
+// (cudaMalloc; the caller owns *d_list and frees it with cudaFree).
+int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* err, int errlen);
 // Launch on `stream`.  `num_sms` = multiprocessor count of the current device.
 int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream);
 // One-time (per process) kernel attribute setup; returns cudaError_t as int.

@@ -205,50 +205,68 @@ __global__ void __launch_bounds__(1024) accum_loss_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------------------
 constexpr int COLSUM_RS = 32;  // row splits
-// block (32, 8): x = column pair inside a 64-column group, y = row lane
+// Single launch, deterministic: block (32, 8) sums a row range of one 64-column group (x = column pair,
+// y = row lane), writes its partial, and the LAST block to finish a column group adds the COLSUM_RS
+// partials in fixed order into out[] (threadfence + counter; counters self-reset).
 __global__ void __launch_bounds__(256)
-colsum_stage1_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld,
-                     int rows, float* __restrict__ ws) {
+colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld, int rows,
+              int cols, float* __restrict__ ws, unsigned int* __restrict__ counters, float* __restrict__ out) {
   __shared__ float sm[8][64];
+  __shared__ unsigned int last;
   const int col = blockIdx.x * 64 + threadIdx.x * 2;
   const int rs = blockIdx.y;
   const int per = (rows + COLSUM_RS - 1) / COLSUM_RS;
   const int r0 = rs * per, r1 = min(rows, r0 + per);
-  float a0 = 0.f, a1 = 0.f;
+  float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
   if (col < ld) {
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+    int r = r0 + threadIdx.y;
+    for (; r + 8 < r1; r += 16) {  // two independent accumulation chains
+      const size_t o0 = static_cast<size_t>(r) * ld + col, o1 = static_cast<size_t>(r + 8) * ld + col;
+      const uint32_t h0 = __ldg(reinterpret_cast<const uint32_t*>(hi + o0));
+      const uint32_t h1 = __ldg(reinterpret_cast<const uint32_t*>(hi + o1));
+      a0 += bf_lo(h0); a1 += bf_hi(h0); c0 += bf_lo(h1); c1 += bf_hi(h1);
+      if (lo) {
+        const uint32_t l0 = __ldg(reinterpret_cast<const uint32_t*>(lo + o0));
+        const uint32_t l1 = __ldg(reinterpret_cast<const uint32_t*>(lo + o1));
+        a0 += bf_lo(l0); a1 += bf_hi(l0); c0 += bf_lo(l1); c1 += bf_hi(l1);
+      }
+    }
+    for (; r < r1; r += 8) {
       const size_t o = static_cast<size_t>(r) * ld + col;
       const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + o));
-      a0 += bf_lo(h);
-      a1 += bf_hi(h);
+      a0 += bf_lo(h); a1 += bf_hi(h);
       if (lo) {
         const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + o));
-        a0 += bf_lo(l);
-        a1 += bf_hi(l);
+        a0 += bf_lo(l); a1 += bf_hi(l);
       }
     }
   }
-  sm[threadIdx.y][threadIdx.x * 2] = a0;
-  sm[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  sm[threadIdx.y][threadIdx.x * 2] = a0 + c0;
+  sm[threadIdx.y][threadIdx.x * 2 + 1] = a1 + c1;
   __syncthreads();
-  if (threadIdx.y == 0) {
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 64) {
+    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int c = threadIdx.x * 2 + k;
+    for (int y = 0; y < 8; ++y) s += sm[y][t];
+    if (blockIdx.x * 64 + t < ld) ws[static_cast<size_t>(rs) * ld + blockIdx.x * 64 + t] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = atomicAdd(&counters[blockIdx.x], 1u);
+  __syncthreads();
+  if (last != COLSUM_RS - 1) return;
+  __threadfence();
+  if (t < 64) {
+    const int c = blockIdx.x * 64 + t;
+    if (c < cols) {
       float s = 0.f;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) s += sm[y][c];
-      if (blockIdx.x * 64 + c < ld) ws[static_cast<size_t>(rs) * ld + blockIdx.x * 64 + c] = s;
+#pragma unroll 8
+      for (int r = 0; r < COLSUM_RS; ++r) s += __ldcg(ws + static_cast<size_t>(r) * ld + c);
+      out[c] += s;
     }
   }
-}
-__global__ void colsum_stage2_kernel(const float* __restrict__ ws, int ld, int cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < COLSUM_RS; ++r) s += ws[static_cast<size_t>(r) * ld + c];
-  out[c] += s;
+  if (t == 0) counters[blockIdx.x] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,9 +642,12 @@ int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st) {
 int k_colsum_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int rows, int cols, float* ws,
                   float* out, cudaStream_t st) {
   if (rows <= 0) return 0;
+  // ws layout: 1024 self-resetting counters (one per 64-column group, zero-initialised) at a FIXED place,
+  // then [COLSUM_RS * ld] partials (calls with different ld must not clobber the counters)
+  if (ld > 65536) return static_cast<int>(cudaErrorInvalidValue);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   dim3 grid((ld + 63) / 64, COLSUM_RS), block(32, 8);
-  colsum_stage1_kernel<<<grid, block, 0, st>>>(hi, lo, ld, rows, ws);
-  colsum_stage2_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, ld, cols, out);
+  colsum_kernel<<<grid, block, 0, st>>>(hi, lo, ld, rows, cols, ws + 1024, counters, out);
   return static_cast<int>(cudaGetLastError());
 }
 

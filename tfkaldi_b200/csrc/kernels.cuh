@@ -32,7 +32,8 @@ int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int 
 // acc[0] += sum(row_loss[0..B)) (fixed-order, double);  acc[1] += B
 int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st);
 
-// out[n] += sum over rows of (hi + lo)[row, n]; deterministic two-stage; ws >= 32*ld floats.
+// out[n] += sum over rows of (hi + lo)[row, n]; deterministic, one launch.
+// ws: zero-initialised scratch of >= 1024 + 32*ld floats (self-resetting counters, then partials).
 int k_colsum_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int rows, int cols,
                   float* ws, float* out, cudaStream_t st);
 

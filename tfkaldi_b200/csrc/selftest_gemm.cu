@@ -30,6 +30,17 @@ using namespace tfk;
 static int g_sms = 148;
 static int* g_sched = nullptr;
 static int g_fail = 0;
+static int g_two_cta = 0;
+static std::vector<int*> g_lists;
+
+static int build(const GemmSpec* s, int n, GemmParams* P, char* err, int errlen) {
+  int rc = gemm_build_params(s, n, g_sched, P, err, errlen, g_two_cta);
+  if (rc) return rc;
+  int* d = nullptr;
+  rc = gemm_upload_tile_lists(P, g_sms, &d, err, errlen);
+  if (d) g_lists.push_back(d);
+  return rc;
+}
 
 static float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
@@ -69,6 +80,7 @@ struct Case {
   int nsplit;
   int out_kind;
   bool bias, relu, mask, stats, dropout;
+  int ksplit = 1;
 };
 
 // reference element (double accumulate). A(m,k), B(n,k) accessors honour storage majorness.
@@ -130,7 +142,7 @@ static bool run_case(const Case& c, std::mt19937& rng, int nsamples) {
   s.M = c.M; s.N = c.N; s.K = c.K;
   s.A_hi = A.d_hi; s.A_lo = A.d_lo; s.lda = ldA; s.a_mn = c.a_mn;
   s.B_hi = B.d_hi; s.B_lo = B.d_lo; s.ldb = ldB; s.b_mn = c.b_mn;
-  s.nsplit = c.nsplit; s.out_kind = c.out_kind;
+  s.nsplit = c.nsplit; s.out_kind = c.out_kind; s.ksplit = c.ksplit;
   s.D_hi = D_hi; s.D_lo = D_lo; s.ldd = ldd;
   s.bias = dbias; s.relu = c.relu;
   if (c.mask) { s.mask_src = Mk.d_hi; s.mask_ld = ldm; s.scale = 2.0f; }
@@ -139,7 +151,7 @@ static bool run_case(const Case& c, std::mt19937& rng, int nsamples) {
 
   GemmParams P;
   char err[256] = {0};
-  int rc = gemm_build_params(&s, 1, g_sched, &P, err, sizeof(err));
+  int rc = build(&s, 1, &P, err, sizeof(err));
   if (rc) { printf("[%s] build_params failed: %s\n", c.name, err); g_fail++; return false; }
   const int reps = c.out_kind == OUT_F32_REDADD ? 2 : 1;
   for (int i = 0; i < reps; ++i) {
@@ -228,8 +240,8 @@ static bool run_case(const Case& c, std::mt19937& rng, int nsamples) {
     }
   }
   const bool ok = bad == 0 && pad_bad == 0 && stat_bad == 0;
-  printf("[%s] %-44s M=%d N=%d K=%d  checked=%d max_err=%.3e (max|ref|=%.2f) bad=%d pad_bad=%d stat_bad=%d\n",
-         ok ? "PASS" : "FAIL", c.name, c.M, c.N, c.K, total, max_err, max_ref, bad, pad_bad, stat_bad);
+  printf("[%s]%s %-44s M=%d N=%d K=%d  checked=%d max_err=%.3e (max|ref|=%.2f) bad=%d pad_bad=%d stat_bad=%d\n",
+         ok ? "PASS" : "FAIL", g_two_cta ? "[2cta]" : "      ", c.name, c.M, c.N, c.K, total, max_err, max_ref, bad, pad_bad, stat_bad);
   if (!ok) g_fail++;
   free_mat(A); free_mat(B);
   if (c.mask) free_mat(Mk);
@@ -257,7 +269,7 @@ static void run_fused_bwd(int Bsz, int Kin, int Nout, int nsplit, std::mt19937& 
   s[1].nsplit = nsplit; s[1].out_kind = split ? OUT_BF16_SPLIT : OUT_BF16; s[1].D_hi = dX_hi; s[1].D_lo = dX_lo; s[1].ldd = Kin;
   s[1].mask_src = X.d_hi; s[1].mask_ld = Kin; s[1].scale = 1.0f;
   GemmParams P; char err[256];
-  if (gemm_build_params(s, 2, g_sched, &P, err, sizeof(err))) { printf("fused build failed: %s\n", err); g_fail++; return; }
+  if (build(s, 2, &P, err, sizeof(err))) { printf("fused build failed: %s\n", err); g_fail++; return; }
   int rc = gemm_launch(P, g_sms, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc || e != cudaSuccess) { printf("fused bwd kernel failed: %d %s\n", rc, cudaGetErrorString(e)); exit(3); }
@@ -281,7 +293,7 @@ static void run_fused_bwd(int Bsz, int Kin, int Nout, int nsplit, std::mt19937& 
       if (er > (split ? 2e-5 : 4e-3) * std::fabs(acc) + 1e-4) { if (bad < 5) printf("   dgrad mismatch (%d,%d) %.6f vs %.6f\n", b, k, acc, got); ++bad; }
       maxe = std::max(maxe, er); }
   }
-  printf("[%s] fused wgrad+dgrad B=%d K=%d N=%d nsplit=%d  max_err=%.3e bad=%d\n", bad ? "FAIL" : "PASS", Bsz, Kin, Nout, nsplit, maxe, bad);
+  printf("[%s]%s fused wgrad+dgrad B=%d K=%d N=%d nsplit=%d  max_err=%.3e bad=%d\n", bad ? "FAIL" : "PASS", g_two_cta ? "[2cta]" : "      ", Bsz, Kin, Nout, nsplit, maxe, bad);
   if (bad) g_fail++;
   if (time_it) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -293,6 +305,21 @@ static void run_fused_bwd(int Bsz, int Kin, int Nout, int nsplit, std::mt19937& 
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= it;
     const double fl = 2.0 * 2.0 * Bsz * (double)Kin * Nout * nsplit;
     printf("       fused bwd: %.1f us  %.1f TFLOP/s (bf16 MMA flops, nsplit=%d)\n", ms * 1e3, fl / ms / 1e9, nsplit);
+    // the same two problems as two back-to-back launches
+    GemmParams P0, P1;
+    if (!build(&s[0], 1, &P0, err, sizeof(err)) && !build(&s[1], 1, &P1, err, sizeof(err))) {
+      for (int i = 0; i < 3; ++i) { gemm_launch(P0, g_sms, 0); gemm_launch(P1, g_sms, 0); }
+      cudaEventRecord(e0);
+      for (int i = 0; i < it; ++i) { gemm_launch(P0, g_sms, 0); gemm_launch(P1, g_sms, 0); }
+      cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&ms, e0, e1); ms /= it;
+      printf("       separate wgrad + dgrad launches: %.1f us  %.1f TFLOP/s\n", ms * 1e3, fl / ms / 1e9);
+      cudaEventRecord(e0);
+      for (int i = 0; i < it; ++i) { gemm_launch(P1, g_sms, 0); gemm_launch(P0, g_sms, 0); }
+      cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&ms, e0, e1); ms /= it;
+      printf("       separate dgrad + wgrad launches: %.1f us  %.1f TFLOP/s\n", ms * 1e3, fl / ms / 1e9);
+    }
   }
   free_mat(X); free_mat(dZ); free_mat(W); cudaFree(G); cudaFree(dX_hi); cudaFree(dX_lo);
 }
@@ -309,7 +336,7 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   s.B_hi = B.d_hi; s.B_lo = B.d_lo; s.ldb = B.ld; s.b_mn = b_mn;
   s.nsplit = nsplit; s.out_kind = out_kind; s.D_hi = D; s.D_lo = Dl; s.ldd = N; s.bias = bias; s.relu = !f32out;
   GemmParams P; char err[256];
-  if (gemm_build_params(&s, 1, g_sched, &P, err, sizeof(err))) { printf("bench build failed %s\n", err); return; }
+  if (build(&s, 1, &P, err, sizeof(err))) { printf("bench build failed %s\n", err); return; }
   for (int i = 0; i < 3; ++i) gemm_launch(P, g_sms, 0);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -318,7 +345,7 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   for (int i = 0; i < it; ++i) gemm_launch(P, g_sms, 0);
   cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= it;
-  printf("[BENCH] %-34s M=%d N=%d K=%d nsplit=%d: %8.1f us  %7.1f TFLOP/s (algorithmic 2MNK: %.1f)\n", name, M, N, K, nsplit,
+  printf("[BENCH]%s %-34s M=%d N=%d K=%d nsplit=%d: %8.1f us  %7.1f TFLOP/s (algorithmic 2MNK: %.1f)\n", g_two_cta ? "[2cta]" : "      ", name, M, N, K, nsplit,
          ms * 1e3, 2.0 * M * N * (double)K * nsplit / ms / 1e9, 2.0 * M * N * (double)K / ms / 1e9);
   free_mat(A); free_mat(B); cudaFree(D); cudaFree(Dl); cudaFree(bias);
 }
@@ -335,6 +362,7 @@ int main(int argc, char** argv) {
   std::mt19937 rng(1234);
   const int NS = 20000;
 
+  for (g_two_cta = (argc > 2 ? atoi(argv[2]) : 0); g_two_cta <= (argc > 3 ? atoi(argv[3]) : 1); ++g_two_cta) {
   if (mode != "bench") {
     std::vector<Case> cases = {
         // name, M,N,K, a_mn,b_mn, nsplit, out, bias,relu,mask,stats,dropout
@@ -355,6 +383,8 @@ int main(int argc, char** argv) {
         {"fwd bn-stats split", 300, 512, 440, 0, 1, 3, OUT_BF16_SPLIT, true, false, false, true, false},
         {"fwd relu+dropout", 256, 512, 128, 0, 1, 1, OUT_BF16, true, true, false, false, true},
         {"fwd many tiles (persistent loop)", 2048, 2048, 256, 0, 1, 1, OUT_BF16, true, true, false, false, false},
+        {"wgrad split-K x5 ragged", 440, 300, 8192 + 40, 1, 1, 1, OUT_F32_REDADD, false, false, false, false, false, 5},
+        {"wgrad split-K x3 bf16x3", 256, 256, 2048, 1, 1, 3, OUT_F32_REDADD, false, false, false, false, false, 3},
     };
     for (auto& c : cases) run_case(c, rng, NS);
     run_fused_bwd(512, 256, 512, 1, rng, 300, false);
@@ -378,6 +408,7 @@ int main(int argc, char** argv) {
     bench_case("wgrad hidden MN/MN redadd", 2048, 2048, 8192, 1, 1, OUT_F32_REDADD, 1, rng);
     bench_case("fwd hidden K/MN x3 split", 8192, 2048, 2048, 0, 1, OUT_BF16_SPLIT, 3, rng);
     bench_case("square 8192^3 K/K bf16 (vs cuBLAS peak)", 8192, 8192, 8192, 0, 0, OUT_BF16, 1, rng);
+  }
   }
   printf("selftest_gemm: %s (%d failures)\n", g_fail ? "FAILED" : "ALL PASS", g_fail);
   return g_fail ? 1 : 0;

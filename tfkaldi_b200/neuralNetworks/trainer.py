@@ -86,6 +86,26 @@ class _Stager(object):
         self.used[k] = True
         return k, self.dev_x[k][:n], self.dev_y[k][:n]
 
+    def stage_pinned(self, x, y, make_current_wait=True):
+        """x [B, I] float32 / y [B] int32 torch tensors already in pinned host memory: H2D straight
+        from the caller's buffers on the copy stream (no host-side repacking)"""
+        k = self.turn
+        self.turn ^= 1
+        n = x.shape[0]
+        if n > self.capacity:
+            raise ValueError("micro-batch of %d frames exceeds the staging capacity %d" % (n, self.capacity))
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.used[k]:
+                self.copy_stream.wait_event(self.consumed[k])
+            self.dev_x[k][:n].copy_(x, non_blocking=True)
+            self.dev_y[k][:n].copy_(y, non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        if make_current_wait:
+            compute.wait_event(self.copied[k])
+        self.used[k] = True
+        return k, self.dev_x[k][:n], self.dev_y[k][:n]
+
     def release(self, k):
         self.consumed[k].record(torch.cuda.current_stream(self.device))
 
@@ -202,17 +222,38 @@ class Trainer(object, metaclass=ABCMeta):
             self._stager.release(k)
         return self._apply()
 
-    def update_packed(self, x, y, want_loss=True):
+    def prefetch(self, x, y):
+        """start the host->device copy of the NEXT packed batch (pinned float32 / int32 tensors) on the
+        copy stream so it overlaps the step in flight; the next update_packed(x, y) with the same tensors
+        consumes it"""
+        if self._stager is None:
+            self._stager = _Stager(self.engine.device, self.input_dim, self.max_frames)
+        k, dx, dy = self._stager.stage_pinned(x, y, make_current_wait=False)
+        self._prefetched = (x.data_ptr(), y.data_ptr(), k, dx, dy)
+
+    def update_packed(self, x, y, want_loss=True, prefetch=None):
         """fast path: one micro-batch already packed as x [B, I] float32 / y [B] int (pinned host tensors,
         numpy arrays or device tensors); same arithmetic as update()"""
         if isinstance(x, torch.Tensor) and x.is_cuda:
             self.engine.accumulate(x, y)
         else:
-            if isinstance(x, torch.Tensor):
-                x, y = x.numpy(), y.numpy()
-            k, dx, dy = self._stage(x, y)
+            if self._stager is None:
+                self._stager = _Stager(self.engine.device, self.input_dim, self.max_frames)
+            pre = getattr(self, "_prefetched", None)
+            if pre is not None and isinstance(x, torch.Tensor) and pre[0] == x.data_ptr() and pre[1] == y.data_ptr():
+                _, _, k, dx, dy = pre
+                self._prefetched = None
+                torch.cuda.current_stream(self.engine.device).wait_event(self._stager.copied[k])
+            elif isinstance(x, torch.Tensor) and x.is_pinned() and y.is_pinned() and x.dtype == torch.float32 and y.dtype == torch.int32:
+                k, dx, dy = self._stager.stage_pinned(x, y)
+            else:
+                if isinstance(x, torch.Tensor):
+                    x, y = x.numpy(), y.numpy()
+                k, dx, dy = self._stager.stage(x, y)
             self.engine.accumulate(dx, dy)
             self._stager.release(k)
+        if prefetch is not None:
+            self.prefetch(*prefetch)  # next batch's H2D overlaps this step's kernels
         return self._apply(want_loss)
 
     def _apply(self, want_loss=True):
