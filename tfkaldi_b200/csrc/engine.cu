@@ -80,6 +80,8 @@ struct Layer {
   float *bn_mean = nullptr, *bn_rstd = nullptr;          // statistics used by the last forward
   float* bn_sums = nullptr;                              // [2*ldn] backward column sums
   __nv_bfloat16 *z_hi = nullptr, *z_lo = nullptr;        // pre-BN linear output [maxB, ldn]
+  uint32_t* maskbits = nullptr;  // [ceil(ldn/32), maxB] gradient-pass bits written by the forward epilogue
+  float* db_part = nullptr;  // [maxB/32 + 8, ldn] bias-gradient partials written by the dgrad epilogue above
 };
 
 struct Plan {  // TMA descriptors (+ CTA-pair work lists) for one (frames, active layers) shape
@@ -271,6 +273,9 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
         s.D_hi = h->act_hi[l + 1]; s.D_lo = h->act_lo[l + 1]; s.ldd = ly.ldn;
         s.relu = relu;
         if (train && drop) { s.keep = h->cfg.keep_prob; s.seed = 0; }
+        if (train && (relu || drop)) {
+          s.mask_bits_out = ly.maskbits; s.mask_bits_ld = h->cfg.max_frames; s.mask_nonzero = relu ? 0 : 1;
+        }
       }
       GemmParams& gp = train ? plan.fwd_train[l] : plan.fwd_eval[l];
       TFK_TRY(finish_params(h, plan, &s, 1, &gp, "forward", l));
@@ -311,9 +316,17 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       s[1].out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
       s[1].D_hi = h->dA_hi[dst]; s[1].D_lo = h->dA_lo[dst]; s[1].ldd = h->layers[lower].ldn;
       if (relu || drop) {
-        s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
+        if (h->layers[lower].bn) {  // activation written by bn_apply: test the stored forward output
+          s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
+        } else {                    // 1 bit per unit, written by the forward epilogue
+          s[1].mask_bits_in = h->layers[lower].maskbits; s[1].mask_bits_ld = h->cfg.max_frames;
+        }
         s[1].mask_nonzero = relu ? 0 : 1;
         s[1].scale = drop ? 1.0f / h->cfg.keep_prob : 1.0f;
+      }
+      if (!h->layers[lower].bn) {  // dz of the layer below is final here: take its column sums for free
+        s[1].colsum_part = h->layers[lower].db_part;
+        s[1].colsum_ld = h->layers[lower].ldn;
       }
       nspec = 2;
     }
@@ -384,7 +397,7 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
 
 // backward of layer l given dZ_l (hidden: in dA[(L-1-l)&1], as d(loss)/d(layer OUTPUT after mask) for BN)
 int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
-                   const GemmParams* gemm_override = nullptr) {
+                   const GemmParams* gemm_override = nullptr, bool fused_colsum = false) {
   const int L = h->L;
   Layer& ly = h->layers[l];
   __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
@@ -397,7 +410,7 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
     TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
                                  ly.bn_sums, st));
   }
-  {
+  if (!fused_colsum || !ly.hidden || ly.bn) {
     TimerScope ts(h, st, TFK_TIMER_COLSUM);
     TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws_colsum, h->G + ly.off_b, st));
   }
@@ -491,8 +504,24 @@ int ce_and_backward(tfk_handle* h, Plan& plan, const int32_t* labels, int B, boo
     TFK_LAUNCH(h, k_accum_loss(h->row_loss, B, h->acc, st));
   }
   if (!backward) return TFK_OK;
-  TFK_TRY(backward_layer(h, plan, B, h->L, st));
-  for (int l = h->active - 1; l >= 0; --l) TFK_TRY(backward_layer(h, plan, B, l, st));
+  TFK_TRY(backward_layer(h, plan, B, h->L, st, nullptr, true));
+  for (int l = h->active - 1; l >= 0; --l) TFK_TRY(backward_layer(h, plan, B, l, st, nullptr, true));
+  {
+    // bias gradients of the non-BN hidden layers: finish the column sums their dgrad epilogues started
+    const float* parts[64];
+    float* outs[64];
+    int n = 0;
+    for (int l = 0; l < h->active; ++l)
+      if (!h->layers[l].bn) {
+        parts[n] = h->layers[l].db_part;
+        outs[n] = h->G + h->layers[l].off_b;
+        ++n;
+      }
+    if (n > 0) {
+      TimerScope ts(h, st, TFK_TIMER_COLSUM);
+      TFK_LAUNCH(h, k_colsum_finalize(parts, outs, n, (B + 31) / 32, h->ldh, h->cfg.hidden_dim, st));
+    }
+  }
   return TFK_OK;
 }
 
@@ -641,6 +670,12 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     if (h->x3) CREATE_TRY(dev_alloc(h, &h->act_lo[l], n));
   }
   for (int l = 0; l < L; ++l) {
+    if (!h->layers[l].bn) {
+      CREATE_TRY(dev_alloc(h, &h->layers[l].db_part, static_cast<size_t>(maxB / 32 + 8) * h->layers[l].ldn));
+      CREATE_TRY(dev_alloc(h, &h->layers[l].maskbits, static_cast<size_t>((h->layers[l].ldn + 31) / 32 + 8) * maxB));
+    }
+  }
+  for (int l = 0; l < L; ++l) {
     Layer& ly = h->layers[l];
     if (!ly.bn) continue;
     CREATE_TRY(dev_alloc(h, &ly.z_hi, static_cast<size_t>(maxB) * ly.ldn));
@@ -669,7 +704,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     CREATE_TRY(dev_alloc(h, &h->bn_pq, n));
   }
   CREATE_TRY(dev_alloc(h, &h->ws, 64 * static_cast<size_t>(h->ldmax)));        // bn backward partials
-  CREATE_TRY(dev_alloc(h, &h->ws_colsum, 1024 + 32 * static_cast<size_t>(h->ldmax)));  // colsum counters + partials
+  CREATE_TRY(dev_alloc(h, &h->ws_colsum, 1024 + 64 * static_cast<size_t>(h->ldmax)));  // colsum counters + partials
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
   {

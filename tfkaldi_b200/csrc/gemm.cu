@@ -169,6 +169,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         v[4 * j + 3] = ((rnd.w >> 8) >= pr.drop_thr) ? v[4 * j + 3] * pr.keep_inv : 0.f;
       }
     }
+    if (pr.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool pass = pr.mask_nonzero ? (v[j] != 0.f) : (v[j] > 0.f);
+        bits |= (pass ? 1u : 0u) << j;
+      }
+      if (row_ok) pr.mask_bits_out[static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row] = bits;
+    }
+    if (pr.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
+      const uint32_t bits = row_ok ? __ldg(pr.mask_bits_in + static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row) : 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * pr.scale : 0.f;
+    }
     if (pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
       const __nv_bfloat16* mp = pr.mask_src + static_cast<size_t>(row) * pr.mask_ld + col0;
       if (row_ok && col0 + 32 <= pr.N) {
@@ -195,6 +209,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
           v[j] = (pr.mask_nonzero ? (mv != 0.f) : (mv > 0.f)) ? v[j] * pr.scale : 0.f;
         }
       }
+    }
+
+    if (pr.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = row_ok ? v[j] : 0.f;
+      const float tot = warp_transpose_reduce(t, lane);
+      const int col = col0 + static_cast<int>(lane);
+      if (col < pr.N) pr.colsum_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
     }
 
     if constexpr (OUT == OUT_F32 || OUT == OUT_F32_REDADD) {
@@ -819,6 +842,9 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.relu = s.relu;
     p.mask_ld = s.mask_ld;
     p.mask_nonzero = s.mask_nonzero;
+    p.mask_bits_out = s.mask_bits_out;
+    p.mask_bits_in = s.mask_bits_in;
+    p.mask_bits_ld = s.mask_bits_ld;
     p.scale = s.scale;
     p.keep_inv = 1.0f / s.keep;
     p.drop_thr = (s.keep < 1.0f) ? dropout_threshold(s.keep) : 0u;
@@ -828,6 +854,8 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.stat_sum = s.stat_sum;
     p.stat_sq = s.stat_sq;
     p.stat_ld = s.stat_ld;
+    p.colsum_part = s.colsum_part;
+    p.colsum_ld = s.colsum_ld;
     p.tiles_m = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     p.tiles_n = (s.N + BN - 1) / BN;
     p.tile_begin = tile_begin;

@@ -54,6 +54,12 @@ struct GemmSpec {
   int mask_ld = 0;
   int mask_nonzero = 0;  // 0: pass where mask_src > 0 (relu);  1: pass where mask_src != 0 (linear+dropout)
   float scale = 1.0f;
+  // Compact alternative to mask_src: 1 bit per element, word (col/32, row) at bits[(col/32)*mask_bits_ld + row]
+  // (chunk-major so a warp's 32 rows read/write 128 contiguous bytes).  The forward epilogue WRITES it
+  // (bit = stored activation passes gradient: > 0, or != 0 with mask_nonzero), the dgrad epilogue READS it.
+  uint32_t* mask_bits_out = nullptr;
+  const uint32_t* mask_bits_in = nullptr;
+  int mask_bits_ld = 0;
   // forward dropout (reference: classifiers/activation.py:140-141): keep<1 => v = v/keep * floor(keep+u)
   float keep = 1.0f;
   unsigned long long seed = 0;  // Philox key; counter = row*N + col
@@ -61,6 +67,10 @@ struct GemmSpec {
   float* stat_sum = nullptr;  // [tiles_m, stat_ld]
   float* stat_sq = nullptr;
   int stat_ld = 0;
+  // per-(32-row group, column) sums of the FINAL stored value (after mask / relu / dropout): the bias
+  // gradient of the layer below falls out of the dgrad epilogue.  [ceil(M/128)*4, colsum_ld]
+  float* colsum_part = nullptr;
+  int colsum_ld = 0;
 };
 
 struct alignas(64) GemmProblem {
@@ -74,10 +84,15 @@ struct alignas(64) GemmProblem {
   unsigned int drop_thr;  // keep element iff (philox >> 8) >= drop_thr; 0 => no dropout
   const float* bias;
   const __nv_bfloat16* mask_src;
+  uint32_t* mask_bits_out;
+  const uint32_t* mask_bits_in;
+  int mask_bits_ld;
   unsigned long long seed;
   float* stat_sum;
   float* stat_sq;
   int stat_ld;
+  float* colsum_part;
+  int colsum_ld;
   int tiles_m, tiles_n, tile_begin, num_kb;
   int ksplit, kb_per_split;
 };

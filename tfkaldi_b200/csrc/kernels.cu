@@ -204,69 +204,86 @@ __global__ void __launch_bounds__(1024) accum_loss_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int COLSUM_RS = 32;  // row splits
-// Single launch, deterministic: block (32, 8) sums a row range of one 64-column group (x = column pair,
-// y = row lane), writes its partial, and the LAST block to finish a column group adds the COLSUM_RS
-// partials in fixed order into out[] (threadfence + counter; counters self-reset).
+constexpr int COLSUM_RS = 32;   // row splits of the BN-backward reductions
+constexpr int COLSUM2_RS = 64;  // row splits of colsum_kernel
+// Single launch, deterministic.  A warp reads 256 consecutive columns (16 B per lane) of one row per
+// load; a block's 8 warps stride over its row range; the LAST block to finish a 256-column group adds
+// the COLSUM2_RS partials in fixed order into out[] (threadfence + self-resetting counter).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int ld, int rows,
               int cols, float* __restrict__ ws, unsigned int* __restrict__ counters, float* __restrict__ out) {
-  __shared__ float sm[8][64];
+  __shared__ float sm[8][256];
   __shared__ unsigned int last;
-  const int col = blockIdx.x * 64 + threadIdx.x * 2;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int rs = blockIdx.y;
-  const int per = (rows + COLSUM_RS - 1) / COLSUM_RS;
+  const int per = (rows + COLSUM2_RS - 1) / COLSUM2_RS;
   const int r0 = rs * per, r1 = min(rows, r0 + per);
-  float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < ld) {
-    int r = r0 + threadIdx.y;
-    for (; r + 8 < r1; r += 16) {  // two independent accumulation chains
-      const size_t o0 = static_cast<size_t>(r) * ld + col, o1 = static_cast<size_t>(r + 8) * ld + col;
-      const uint32_t h0 = __ldg(reinterpret_cast<const uint32_t*>(hi + o0));
-      const uint32_t h1 = __ldg(reinterpret_cast<const uint32_t*>(hi + o1));
-      a0 += bf_lo(h0); a1 += bf_hi(h0); c0 += bf_lo(h1); c1 += bf_hi(h1);
-      if (lo) {
-        const uint32_t l0 = __ldg(reinterpret_cast<const uint32_t*>(lo + o0));
-        const uint32_t l1 = __ldg(reinterpret_cast<const uint32_t*>(lo + o1));
-        a0 += bf_lo(l0); a1 += bf_hi(l0); c0 += bf_lo(l1); c1 += bf_hi(l1);
-      }
-    }
-    for (; r < r1; r += 8) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
       const size_t o = static_cast<size_t>(r) * ld + col;
-      const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + o));
-      a0 += bf_lo(h); a1 += bf_hi(h);
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + o));
+      acc[0] += bf_lo(h.x); acc[1] += bf_hi(h.x); acc[2] += bf_lo(h.y); acc[3] += bf_hi(h.y);
+      acc[4] += bf_lo(h.z); acc[5] += bf_hi(h.z); acc[6] += bf_lo(h.w); acc[7] += bf_hi(h.w);
       if (lo) {
-        const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + o));
-        a0 += bf_lo(l); a1 += bf_hi(l);
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + o));
+        acc[0] += bf_lo(l.x); acc[1] += bf_hi(l.x); acc[2] += bf_lo(l.y); acc[3] += bf_hi(l.y);
+        acc[4] += bf_lo(l.z); acc[5] += bf_hi(l.z); acc[6] += bf_lo(l.w); acc[7] += bf_hi(l.w);
       }
     }
   }
-  sm[threadIdx.y][threadIdx.x * 2] = a0 + c0;
-  sm[threadIdx.y][threadIdx.x * 2 + 1] = a1 + c1;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sm[w][lane * 8 + k] = acc[k];
   __syncthreads();
-  const int t = threadIdx.y * 32 + threadIdx.x;
-  if (t < 64) {
+  const int t = threadIdx.x;
+  {
     float s = 0.f;
 #pragma unroll
     for (int y = 0; y < 8; ++y) s += sm[y][t];
-    if (blockIdx.x * 64 + t < ld) ws[static_cast<size_t>(rs) * ld + blockIdx.x * 64 + t] = s;
+    if (blockIdx.x * 256 + t < ld) ws[static_cast<size_t>(rs) * ld + blockIdx.x * 256 + t] = s;
   }
   __threadfence();
   __syncthreads();
   if (t == 0) last = atomicAdd(&counters[blockIdx.x], 1u);
   __syncthreads();
-  if (last != COLSUM_RS - 1) return;
+  if (last != COLSUM2_RS - 1) return;
   __threadfence();
-  if (t < 64) {
-    const int c = blockIdx.x * 64 + t;
-    if (c < cols) {
-      float s = 0.f;
+  const int c = blockIdx.x * 256 + t;
+  if (c < cols) {
+    float s = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < COLSUM_RS; ++r) s += __ldcg(ws + static_cast<size_t>(r) * ld + c);
-      out[c] += s;
-    }
+    for (int r = 0; r < COLSUM2_RS; ++r) s += __ldcg(ws + static_cast<size_t>(r) * ld + c);
+    out[c] += s;
   }
   if (t == 0) counters[blockIdx.x] = 0u;
+}
+
+// out_j[c] += sum over the 32-row groups of part_j[g][c]: finishes the column sums the GEMM epilogue
+// started (bias gradients), for up to 16 layers in one launch (blockIdx.y = job).
+struct ColsumJobs {
+  const float* part[16];
+  float* out[16];
+  int groups, ld, cols, njobs;
+};
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const ColsumJobs J) {
+  __shared__ float sm[4][64];
+  const float* __restrict__ part = J.part[blockIdx.y];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int g0 = threadIdx.x >> 6;  // 4 group lanes
+  float s0 = 0.f, s1 = 0.f;
+  if (c < J.cols) {
+    int g = g0;
+    for (; g + 4 < J.groups; g += 8) {
+      s0 += part[static_cast<size_t>(g) * J.ld + c];
+      s1 += part[static_cast<size_t>(g + 4) * J.ld + c];
+    }
+    for (; g < J.groups; g += 4) s0 += part[static_cast<size_t>(g) * J.ld + c];
+  }
+  sm[g0][threadIdx.x & 63] = s0 + s1;
+  __syncthreads();
+  if (g0 == 0 && c < J.cols) J.out[blockIdx.y][c] += (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -642,12 +659,28 @@ int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st) {
 int k_colsum_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int rows, int cols, float* ws,
                   float* out, cudaStream_t st) {
   if (rows <= 0) return 0;
-  // ws layout: 1024 self-resetting counters (one per 64-column group, zero-initialised) at a FIXED place,
-  // then [COLSUM_RS * ld] partials (calls with different ld must not clobber the counters)
+  // ws layout: 1024 self-resetting counters (one per 256-column group, zero-initialised) at a FIXED place,
+  // then [COLSUM2_RS * ld] partials (calls with different ld must not clobber the counters)
   if (ld > 65536) return static_cast<int>(cudaErrorInvalidValue);
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
-  dim3 grid((ld + 63) / 64, COLSUM_RS), block(32, 8);
-  colsum_kernel<<<grid, block, 0, st>>>(hi, lo, ld, rows, cols, ws + 1024, counters, out);
+  dim3 grid((ld + 255) / 256, COLSUM2_RS);
+  colsum_kernel<<<grid, 256, 0, st>>>(hi, lo, ld, rows, cols, ws + 1024, counters, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, int groups, int ld, int cols,
+                      cudaStream_t st) {
+  for (int j0 = 0; j0 < njobs; j0 += 16) {
+    ColsumJobs J;
+    J.njobs = njobs - j0 < 16 ? njobs - j0 : 16;
+    for (int j = 0; j < J.njobs; ++j) {
+      J.part[j] = parts[j0 + j];
+      J.out[j] = outs[j0 + j];
+    }
+    J.groups = groups; J.ld = ld; J.cols = cols;
+    dim3 grid((cols + 63) / 64, J.njobs);
+    colsum_finalize_kernel<<<grid, 256, 0, st>>>(J);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -33,9 +33,14 @@ int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int 
 int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st);
 
 // out[n] += sum over rows of (hi + lo)[row, n]; deterministic, one launch.
-// ws: zero-initialised scratch of >= 1024 + 32*ld floats (self-resetting counters, then partials).
+// ws: zero-initialised scratch of >= 1024 + 64*ld floats (self-resetting counters, then partials).
 int k_colsum_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, int rows, int cols,
                   float* ws, float* out, cudaStream_t st);
+
+// outs[j][c] += sum_g parts[j][g*ld + c], g < groups: finishes the per-32-row column sums written by the
+// GEMM epilogue (GemmSpec::colsum_part) for njobs layers in one launch.  parts/outs are HOST arrays.
+int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, int groups, int ld, int cols,
+                      cudaStream_t st);
 
 // Mean -> clip[-1,1] -> TF-form Adam -> refresh bf16 shadows -> re-zero the accumulator
 // (reference: neuralNetworks/trainer.py:174-184 and :350).  frames = acc[1] (device double).
