@@ -155,7 +155,14 @@ int tfk_set_dropout_seed(tfk_handle* h, uint64_t seed);
 /* Data parallel (no reference equivalent: a rank plays the role of one utterance micro-batch of
  * trainer.py:310-332).  tfk_comm_unique_id: rank 0 fills 128 bytes; every rank then calls
  * tfk_comm_init with the same id.  After that tfk_apply sums {gradients, batch_loss, num_frames}
- * over ranks (NCCL all-reduce on a private stream, bucketed per layer) before the Adam step. */
+ * over ranks before the (mathematically identical) mean -> clip -> Adam step:
+ *   - default for 2^k ranks ("sharded"): per-layer NCCL reduce-scatter of the weight gradients, each
+ *     rank runs Adam on its 1/n slice of every layer, then all-gathers the bf16 operand copies; the
+ *     small vectors (biases, betas) and {loss, frames} are all-reduced and updated everywhere;
+ *   - TFK_DP_MODE=allreduce (or a non-power-of-two world): all-reduce everything, replicated Adam.
+ * Under the sharded mode the fp32 master weights / Adam slots of a slice live on its owner only:
+ * tfk_get_tensor(TFK_T_WEIGHTS / TFK_T_ADAM_*_W) is then COLLECTIVE (it all-gathers them first), so
+ * every rank must call it, in the same order (checkpointing code that all ranks run does). */
 int tfk_comm_unique_id(uint8_t* id128_host);
 int tfk_comm_init(tfk_handle* h, const uint8_t* id128_host, int rank, int nranks);
 /* Alternative: adopt an existing ncclComm_t (not destroyed by tfk_destroy). */

@@ -38,13 +38,14 @@ def _shards(world):
     return [(rng.standard_normal((n, 440)).astype(np.float32), rng.integers(0, 183, n)) for n in sizes]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     import torch
     import torch.distributed as dist
 
     from tfkaldi_b200.engine import Engine
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["TFK_DP_MODE"] = mode
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     eng = Engine(2, 440, 256, 183, 512, nonlin="linear", precision="bf16x3", device=rank)
@@ -61,7 +62,8 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(600)
-def test_dp_equals_microbatch_accumulation(cuda_device, tmp_path):
+@pytest.mark.parametrize("mode", ["sharded", "allreduce"])
+def test_dp_equals_microbatch_accumulation(cuda_device, tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
 
@@ -71,7 +73,7 @@ def test_dp_equals_microbatch_accumulation(cuda_device, tmp_path):
     if world < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = min(world, 4)
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     single = Engine(2, 440, 256, 183, 512, nonlin="linear", precision="bf16x3", device=0)
     single.load_params(_params())
     losses = []

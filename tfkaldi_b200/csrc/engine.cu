@@ -39,6 +39,8 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -58,14 +60,16 @@ NcclApi& nccl() {
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(dlsym(lib, "ncclReduceScatter"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
   api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(lib, "ncclGroupStart"));
   api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart &&
-           api.GroupEnd;
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.ReduceScatter &&
+           api.AllGather && api.GroupStart && api.GroupEnd;
   return api;
 }
-constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclSum = 0;
+constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclBf16 = 9, kNcclSum = 0;
 
 thread_local std::string g_create_error;
 
@@ -76,6 +80,7 @@ struct Layer {
   int npad = 0;       // padded length of per-column vectors: round_up(N, 256)
   bool hidden = false, bn = false;
   size_t off_w = 0, off_b = 0, off_beta = 0;  // offsets (floats) into the parameter arenas
+  size_t w_count = 0;                         // floats reserved for W (K*ldn rounded up to 1024)
   float *moving_mean = nullptr, *moving_var = nullptr;  // [npad]
   float *bn_mean = nullptr, *bn_rstd = nullptr;          // statistics used by the last forward
   float* bn_sums = nullptr;                              // [2*ldn] backward column sums
@@ -100,6 +105,9 @@ struct tfk_handle {
   int num_sms = 148;
   std::vector<Layer> layers;  // L+1
   size_t arena_n = 0;
+  size_t nW = 0;  // [0, nW): weight regions of all layers; [nW, arena_n): biases and batch-norm betas
+  bool sharded = false;       // data parallel with reduce-scatter -> sharded Adam -> all-gather
+  bool params_synced = true;  // fp32 master weights / Adam slots identical on every rank
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
   __nv_bfloat16 *Sh = nullptr, *Sl = nullptr;
   std::vector<__nv_bfloat16*> act_hi, act_lo;  // [L+1]: act[0] = input, act[l+1] = output of hidden l
@@ -482,10 +490,9 @@ int allreduce_grads(tfk_handle* h, cudaStream_t st) {
     // one bucket per layer, output layer first (the order the backward pass finishes them)
     for (int l = h->L; l >= 0 && rc == 0; --l) {
       const Layer& ly = h->layers[l];
-      const size_t begin = ly.off_w;
-      const size_t end = (l == h->L) ? h->arena_n : h->layers[l + 1].off_w;
-      rc = api.AllReduce(h->G + begin, h->G + begin, end - begin, kNcclFloat, kNcclSum, h->comm, h->comm_stream);
+      rc = api.AllReduce(h->G + ly.off_w, h->G + ly.off_w, ly.w_count, kNcclFloat, kNcclSum, h->comm, h->comm_stream);
     }
+    if (rc == 0) rc = api.AllReduce(h->G + h->nW, h->G + h->nW, h->arena_n - h->nW, kNcclFloat, kNcclSum, h->comm, h->comm_stream);
     if (rc == 0) rc = api.AllReduce(h->acc, h->acc, 2, kNcclDouble, kNcclSum, h->comm, h->comm_stream);
     const int rc2 = api.GroupEnd();
     if (rc || rc2)
@@ -493,6 +500,78 @@ int allreduce_grads(tfk_handle* h, cudaStream_t st) {
   }
   TFK_CUDA(h, cudaEventRecord(h->ev_comm, h->comm_stream));
   TFK_CUDA(h, cudaStreamWaitEvent(st, h->ev_comm, 0));
+  return TFK_OK;
+}
+
+// Sharded data parallelism (ZeRO-1 style): every layer's weight gradient is reduce-scattered (rank r ends
+// up with the global sum of slice r), the small vectors and {loss, frames} are all-reduced.
+int reduce_scatter_grads(tfk_handle* h, cudaStream_t st) {
+  NcclApi& api = nccl();
+  TFK_CUDA(h, cudaEventRecord(h->ev_compute, st));
+  TFK_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+  {
+    TimerScope ts(h, h->comm_stream, TFK_TIMER_ALLREDUCE, h->L + 3);
+    int rc = api.GroupStart();
+    for (int l = h->L; l >= 0 && rc == 0; --l) {
+      const Layer& ly = h->layers[l];
+      const size_t cnt = ly.w_count / h->nranks;
+      rc = api.ReduceScatter(h->G + ly.off_w, h->G + ly.off_w + cnt * h->rank, cnt, kNcclFloat, kNcclSum, h->comm,
+                             h->comm_stream);
+    }
+    if (rc == 0) rc = api.AllReduce(h->G + h->nW, h->G + h->nW, h->arena_n - h->nW, kNcclFloat, kNcclSum, h->comm, h->comm_stream);
+    if (rc == 0) rc = api.AllReduce(h->acc, h->acc, 2, kNcclDouble, kNcclSum, h->comm, h->comm_stream);
+    const int rc2 = api.GroupEnd();
+    if (rc || rc2)
+      return fail(h, TFK_ENCCL, "ncclReduceScatter failed: %s", api.GetErrorString ? api.GetErrorString(rc ? rc : rc2) : "?");
+  }
+  TFK_CUDA(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+  TFK_CUDA(h, cudaStreamWaitEvent(st, h->ev_comm, 0));
+  return TFK_OK;
+}
+
+// after the sharded Adam step: every rank publishes the bf16 operand copies of its weight slices
+int all_gather_shadows(tfk_handle* h, cudaStream_t st) {
+  NcclApi& api = nccl();
+  TFK_CUDA(h, cudaEventRecord(h->ev_compute, st));
+  TFK_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+  {
+    TimerScope ts(h, h->comm_stream, TFK_TIMER_ALLREDUCE, (h->L + 1) * (h->x3 ? 2 : 1));
+    int rc = api.GroupStart();
+    for (int l = 0; l <= h->L && rc == 0; ++l) {  // layer 0 first: the next forward needs it first
+      const Layer& ly = h->layers[l];
+      const size_t cnt = ly.w_count / h->nranks;
+      rc = api.AllGather(h->Sh + ly.off_w + cnt * h->rank, h->Sh + ly.off_w, cnt, kNcclBf16, h->comm, h->comm_stream);
+      if (rc == 0 && h->x3)
+        rc = api.AllGather(h->Sl + ly.off_w + cnt * h->rank, h->Sl + ly.off_w, cnt, kNcclBf16, h->comm, h->comm_stream);
+    }
+    const int rc2 = api.GroupEnd();
+    if (rc || rc2)
+      return fail(h, TFK_ENCCL, "ncclAllGather failed: %s", api.GetErrorString ? api.GetErrorString(rc ? rc : rc2) : "?");
+  }
+  TFK_CUDA(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+  TFK_CUDA(h, cudaStreamWaitEvent(st, h->ev_comm, 0));
+  return TFK_OK;
+}
+
+// collective: make the fp32 master weights and Adam slots of the weight regions identical everywhere
+int sync_sharded_params(tfk_handle* h, cudaStream_t st) {
+  if (!h->sharded || h->params_synced) return TFK_OK;
+  NcclApi& api = nccl();
+  TFK_CUDA(h, cudaEventRecord(h->ev_compute, st));
+  TFK_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+  int rc = api.GroupStart();
+  float* arenas[3] = {h->P, h->M, h->V};
+  for (int a = 0; a < 3 && rc == 0; ++a)
+    for (int l = 0; l <= h->L && rc == 0; ++l) {
+      const Layer& ly = h->layers[l];
+      const size_t cnt = ly.w_count / h->nranks;
+      rc = api.AllGather(arenas[a] + ly.off_w + cnt * h->rank, arenas[a] + ly.off_w, cnt, kNcclFloat, h->comm, h->comm_stream);
+    }
+  const int rc2 = api.GroupEnd();
+  if (rc || rc2) return fail(h, TFK_ENCCL, "parameter all-gather failed: %s", api.GetErrorString ? api.GetErrorString(rc ? rc : rc2) : "?");
+  TFK_CUDA(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+  TFK_CUDA(h, cudaStreamWaitEvent(st, h->ev_comm, 0));
+  h->params_synced = true;
   return TFK_OK;
 }
 
@@ -646,7 +725,15 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     ly.ldn = round_up(ly.N, 8);
     ly.npad = round_up(ly.N, 256);
     ly.bn = ly.hidden && cfg->batch_norm;
-    ly.off_w = off; off += static_cast<size_t>(ly.K) * ly.ldn;
+    // weight regions first (each a multiple of 1024 floats so it splits evenly over 2^k ranks), then the
+    // small per-column vectors: under sharded data parallelism the first part is reduce-scattered and
+    // its Adam step sharded, the second part is all-reduced and replicated
+    ly.w_count = (static_cast<size_t>(ly.K) * ly.ldn + 1023) / 1024 * 1024;
+    ly.off_w = off; off += ly.w_count;
+  }
+  h->nW = off;
+  for (int l = 0; l <= L; ++l) {
+    Layer& ly = h->layers[l];
     ly.off_b = off; off += ly.npad;
     if (ly.bn) { ly.off_beta = off; off += ly.npad; }
   }
@@ -741,6 +828,8 @@ int tfk_get_tensor(tfk_handle* h, int kind, int layer, float* dst, size_t count,
   if (count != static_cast<size_t>(rows) * cols)
     return fail(h, TFK_ESHAPE, "tfk_get_tensor: kind %d layer %d holds %d x %d elements, asked %zu", kind, layer, rows, cols, count);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (kind == TFK_T_WEIGHTS || kind == TFK_T_ADAM_M_W || kind == TFK_T_ADAM_V_W)
+    TFK_TRY(sync_sharded_params(h, st));  // collective under sharded data parallelism (see header)
   TFK_CUDA(h, cudaMemcpy2DAsync(dst, static_cast<size_t>(cols) * 4, base, static_cast<size_t>(ld) * 4,
                                 static_cast<size_t>(cols) * 4, rows, cudaMemcpyDefault, st));
   TFK_CUDA(h, cudaStreamSynchronize(st));
@@ -934,7 +1023,8 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (!h) return TFK_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
-  TFK_TRY(allreduce_grads(h, st));
+  if (h->sharded) TFK_TRY(reduce_scatter_grads(h, st));
+  else TFK_TRY(allreduce_grads(h, st));
   h->global_step += 1;  // apply_gradients(global_step=...)   trainer.py:182-184
   const double t = static_cast<double>(h->global_step);
   const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
@@ -942,8 +1032,31 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   const float lr_t = static_cast<float>(lr_eff * std::sqrt(1.0 - std::pow(b2, t)) / (1.0 - std::pow(b1, t)));
   {
     TimerScope ts(h, st, TFK_TIMER_ADAM);
-    TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, h->arena_n, h->acc, lr_t,
+    size_t off[80], cnt[80];
+    int n = 0;
+    if (h->sharded) {  // this rank's slice of every layer's weights + the replicated small vectors
+      for (int l = 0; l <= h->L; ++l) {
+        const size_t c = h->layers[l].w_count / h->nranks;
+        off[n] = h->layers[l].off_w + c * h->rank; cnt[n] = c; ++n;
+      }
+      off[n] = h->nW; cnt[n] = h->arena_n - h->nW; ++n;
+    } else {
+      off[0] = 0; cnt[0] = h->arena_n; n = 1;
+    }
+    TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, off, cnt, n, h->acc, lr_t,
                          h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
+  }
+  if (h->sharded) {
+    // non-owned gradient slices still hold this rank's local sums: clear them for the next accumulation
+    for (int l = 0; l <= h->L; ++l) {
+      const Layer& ly = h->layers[l];
+      const size_t c = ly.w_count / h->nranks, lo = c * h->rank;
+      if (lo) TFK_CUDA(h, cudaMemsetAsync(h->G + ly.off_w, 0, lo * sizeof(float), st));
+      if (lo + c < ly.w_count)
+        TFK_CUDA(h, cudaMemsetAsync(h->G + ly.off_w + lo + c, 0, (ly.w_count - lo - c) * sizeof(float), st));
+    }
+    TFK_TRY(all_gather_shadows(h, st));
+    h->params_synced = false;
   }
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));  // init_loss / init_num_frames
@@ -1039,6 +1152,8 @@ int tfk_comm_init(tfk_handle* h, const uint8_t* id128_host, int rank, int nranks
   h->own_comm = true;
   h->rank = rank;
   h->nranks = nranks;
+  const char* mode = getenv("TFK_DP_MODE");  // "allreduce" keeps the replicated-Adam path
+  h->sharded = nranks > 1 && (nranks & (nranks - 1)) == 0 && nranks <= 256 && !(mode && strcmp(mode, "allreduce") == 0);
   return setup_comm_streams(h);
 }
 
@@ -1049,6 +1164,8 @@ int tfk_set_comm(tfk_handle* h, void* nccl_comm, int rank, int nranks) {
   h->own_comm = false;
   h->rank = rank;
   h->nranks = nccl_comm ? nranks : 1;
+  const char* mode = getenv("TFK_DP_MODE");
+  h->sharded = h->nranks > 1 && (h->nranks & (h->nranks - 1)) == 0 && h->nranks <= 256 && !(mode && strcmp(mode, "allreduce") == 0);
   return nccl_comm ? setup_comm_streams(h) : TFK_OK;
 }
 

@@ -287,14 +287,23 @@ __global__ void __launch_bounds__(256) colsum_finalize_kernel(const ColsumJobs J
 }
 
 // ------------------------------------------------------------------------------------------------
+struct AdamSegs {
+  unsigned long long off4[64];  // segment start, in float4 units
+  unsigned long long cnt4[64];  // segment length, in float4 units
+  int n;
+};
+// blockIdx.y = segment (the whole arena on one GPU; a rank's slice of every layer + the small
+// replicated region under sharded data parallelism)
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-            uint2* __restrict__ w_hi, uint2* __restrict__ w_lo, size_t n4, const double* __restrict__ acc,
+            uint2* __restrict__ w_hi, uint2* __restrict__ w_lo, const AdamSegs segs, const double* __restrict__ acc,
             float lr_t, float b1, float b2, float eps) {
   const float frames = static_cast<float>(acc[1]);
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const size_t base = segs.off4[blockIdx.y], n4 = segs.cnt4[blockIdx.y];
+  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n4;
+       k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = base + k;
     const float4 gg = g[i];
     float4 mm = m[i], vv = v[i], ww = w[i];
     float gx[4] = {gg.x, gg.y, gg.z, gg.w};
@@ -302,17 +311,17 @@ adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__
     float vx[4] = {vv.x, vv.y, vv.z, vv.w};
     float wx[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float gh = gx[k] / frames;                     // tf.div(grad, num_frames)   trainer.py:174
-      gh = fminf(fmaxf(gh, -1.0f), 1.0f);            // tf.clip_by_value(-1, 1)    trainer.py:178
-      mx[k] += (gh - mx[k]) * omb1;                  // TF ApplyAdam
-      vx[k] += (gh * gh - vx[k]) * omb2;
-      wx[k] -= (mx[k] * lr_t) / (sqrtf(vx[k]) + eps);
+    for (int k2 = 0; k2 < 4; ++k2) {
+      float gh = gx[k2] / frames;                      // tf.div(grad, num_frames)   trainer.py:174
+      gh = fminf(fmaxf(gh, -1.0f), 1.0f);              // tf.clip_by_value(-1, 1)    trainer.py:178
+      mx[k2] += (gh - mx[k2]) * omb1;                  // TF ApplyAdam
+      vx[k2] += (gh * gh - vx[k2]) * omb2;
+      wx[k2] -= (mx[k2] * lr_t) / (sqrtf(vx[k2]) + eps);
     }
     m[i] = make_float4(mx[0], mx[1], mx[2], mx[3]);
     v[i] = make_float4(vx[0], vx[1], vx[2], vx[3]);
     w[i] = make_float4(wx[0], wx[1], wx[2], wx[3]);
-    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);          // init_grads                 trainer.py:350
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);            // init_grads                 trainer.py:350
     uint2 h, l;
     split2(wx[0], wx[1], h.x, l.x);
     split2(wx[2], wx[3], h.y, l.y);
@@ -684,13 +693,27 @@ int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, 
   return static_cast<int>(cudaGetLastError());
 }
 
-int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, size_t n,
-           const double* acc, float lr_t, float beta1, float beta2, float eps, cudaStream_t st) {
-  const size_t n4 = n >> 2;
-  adam_kernel<<<grid_for(n4, 256, 148 * 8), 256, 0, st>>>(
-      reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
-      reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(w_hi), reinterpret_cast<uint2*>(w_lo), n4, acc,
-      lr_t, beta1, beta2, eps);
+int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, const size_t* seg_off,
+           const size_t* seg_cnt, int nseg, const double* acc, float lr_t, float beta1, float beta2, float eps,
+           cudaStream_t st) {
+  for (int s0 = 0; s0 < nseg; s0 += 64) {
+    AdamSegs segs;
+    segs.n = nseg - s0 < 64 ? nseg - s0 : 64;
+    size_t longest = 0;
+    for (int i = 0; i < segs.n; ++i) {
+      segs.off4[i] = seg_off[s0 + i] >> 2;
+      segs.cnt4[i] = seg_cnt[s0 + i] >> 2;
+      longest = segs.cnt4[i] > longest ? segs.cnt4[i] : longest;
+    }
+    if (longest == 0) continue;
+    int per_seg = 148 * 8 / segs.n;
+    if (per_seg < 8) per_seg = 8;
+    dim3 grid(grid_for(longest, 256, per_seg), segs.n);
+    adam_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(g),
+                                      reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                      reinterpret_cast<uint2*>(w_hi), reinterpret_cast<uint2*>(w_lo), segs, acc, lr_t,
+                                      beta1, beta2, eps);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -44,8 +44,11 @@ int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, 
 
 // Mean -> clip[-1,1] -> TF-form Adam -> refresh bf16 shadows -> re-zero the accumulator
 // (reference: neuralNetworks/trainer.py:174-184 and :350).  frames = acc[1] (device double).
-int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, size_t n,
-           const double* acc, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
+// Works on `nseg` segments {offset, count} (floats, multiples of 4) of the flat arenas: the whole arena on
+// one GPU, a rank's slice of every layer under sharded data parallelism.
+int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, const size_t* seg_off,
+           const size_t* seg_cnt, int nseg, const double* acc, float lr_t, float beta1, float beta2, float eps,
+           cudaStream_t st);
 
 // Batch-norm (reference: classifiers/activation.py:159 -> tf.contrib.layers.batch_norm defaults):
 // finalize per-column batch statistics from the GEMM epilogue's 32-row partials, update the moving
