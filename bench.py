@@ -203,6 +203,22 @@ def run_ours(args):
     achieved = train_fl * B / (gemm_ms * 1e-3) / 1e12
     breakdown = {k: round(v[0] / args.steps * 1e3, 1) for k, v in timers.items() if v[1]}  # us per step
 
+    # HBM-bound kernels: algorithmic bytes / in-situ CUDA-event time (SURVEY.md 8d byte counts, adjusted to
+    # what this engine actually stores: bf16 (or bf16 hi+lo) gradients / shadows)
+    nparams = sum(a * b for a, b in zip([c["input_dim"]] + [c["hidden_dim"]] * c["num_layers"], [c["hidden_dim"]] * c["num_layers"] + [O]))
+    sh = 2 if args.precision == "bf16" else 4
+    hbm_bytes = {
+        "adam": (28 + sh) * nparams / max(world, 1) if world > 1 else (28 + sh) * nparams,
+        "softmax_ce": B * O * (4 + sh),
+        "bn": (c["num_layers"] * B * c["hidden_dim"] * (2 * sh + 5 * sh)) if c["batch_norm"] else 0,
+    }
+    hbm = {}
+    for k, nbytes in hbm_bytes.items():
+        if nbytes and timers[k][1]:
+            us = timers[k][0] / args.steps * 1e3
+            hbm[k] = {"bytes_per_step": int(nbytes), "us_per_step": round(us, 1), "gbs": round(nbytes / us / 1e3, 1),
+                      "frac_of_measured_hbm_peak": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3)}
+
     out = None
     if rank == 0:
         frames_total = B * world
@@ -228,12 +244,13 @@ def run_ours(args):
                     "api": "CrossEnthropyTrainer.update_packed(pinned x, pinned labels) -> loss", "last_loss": last_loss},
             "gpu_launches": int(launches * args.steps),
             "gpu_launches_per_step": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "tfk_gemm_kernel (fused FFLayer fwd + fused wgrad/dgrad, %d launches/step)" % gemm_launches,
+            "roofline": {"bound": "tensor", "kernel": "tfk_gemm2_kernel (cta_group::2 CTA pairs; fused FFLayer fwd + fused wgrad/dgrad, %d launches/step)" % gemm_launches,
                          "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
                          "peak_source": peaks["source"] + " (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
                          "algorithmic_flops_per_step": train_fl * B, "kernel_ms_per_step": gemm_ms, "traffic": None,
                          "step_share": gemm_ms / ms_resident, "per_step_us_by_kernel_class": breakdown},
+            "hbm_kernels": hbm,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -336,18 +353,100 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_decode(args):
+    """BASELINE.json configs[4]: trained-shape 6x2048 net, forward-only log-likelihood emission of
+    100k-frame utterances through Decoder + ArkWriter (reference: nnet.py:246-289)."""
+    import tempfile
+
+    import torch
+
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.decoder import Decoder
+    from tfkaldi_b200.processing import ark
+
+    torch.cuda.set_device(0)
+    c = CONFIGS["c2"]
+    T, I, O = 100000, c["input_dim"], c["output_dim"]
+    dnn = DNN(O, c["num_layers"], c["hidden_dim"], act.TfActivation(None, act.relu), False)
+    dec = Decoder(dnn, I, T, precision=args.precision, max_frames=16384)
+    rng = np.random.default_rng(7)
+    dec.engine.load_params(dnn.initial_parameters(I, rng))
+    from tfkaldi_b200 import _lib as L
+
+    dec.engine.set_tensor(L.T_WEIGHTS, c["num_layers"], (rng.standard_normal((c["hidden_dim"], O)) / math.sqrt(c["hidden_dim"])).astype(np.float32))
+    prior = torch.full((O,), 1.0 / O, dtype=torch.float32, device="cuda")
+    x_host = torch.randn((T, I), dtype=torch.float32).pin_memory()
+    x_dev = x_host.cuda()
+    out_dev = torch.empty((T, O), dtype=torch.float32, device="cuda")
+    steps, warm = max(3, args.steps // 20), 3
+    for _ in range(warm):
+        dec.loglik(x_dev, prior, out=out_dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    l0 = dec.engine.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dec.loglik(x_dev, prior, out=out_dev)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (dec.engine.kernel_launches() - l0) // steps
+    clocks = sampler.stop()
+    # end to end: host utterance -> H2D -> forward -> D2H -> ArkWriter (tmpfs if available)
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    writer = ark.ArkWriter(os.path.join(tmp, "feats.scp"), os.path.join(tmp, "likelihoods.ark"))
+    out_host = torch.empty((T, O), dtype=torch.float32).pin_memory()
+    x_np = x_host.numpy()
+    t_e2e = []
+    for i in range(1 + 2):
+        t0 = time.perf_counter()
+        ll = dec.loglik(x_np, prior, out=out_dev)
+        out_host.copy_(ll, non_blocking=False)
+        writer.write_next_utt("utt%d" % i, out_host.numpy())
+        writer.flush()
+        t_e2e.append(time.perf_counter() - t0)
+    writer.close()
+    import shutil
+
+    shutil.rmtree(tmp, ignore_errors=True)
+    _, fwd_fl = flops_per_frame(c)
+    dec.engine.enable_timers(True)
+    for _ in range(steps):
+        dec.loglik(x_dev, prior, out=out_dev)
+    tm = dec.engine.timers()
+    peaks = measured_peaks()
+    gemm_ms = tm["gemm_fwd"][0] / steps
+    print(json.dumps({
+        "metric": "decoder frames/sec (forward-only log-likelihood emission)", "value": T / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "C5: 440-6x2048-1936 DNN, one 100000-frame utterance per step, log(softmax/prior) -> [T,1936] fp32", "frames": T},
+        "e2e": {"value": T / min(t_e2e[1:]), "unit": "frames/s", "seconds_per_utt": min(t_e2e[1:]), "h2d_bytes_per_step": T * I * 4, "d2h_bytes_per_step": T * O * 4,
+                "api": "Decoder.loglik(numpy utterance) -> host -> ArkWriter.write_next_utt (774 MB archive entry)"},
+        "gpu_launches": int(launches * steps), "gpu_launches_per_step": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "tfk_gemm2_kernel (forward)", "achieved": fwd_fl * T / (gemm_ms * 1e-3) / 1e12, "peak": peaks["tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": fwd_fl * T / (gemm_ms * 1e-3) / 1e12 / peaks["tflops_sustained"], "traffic": None,
+                     "per_step_us_by_kernel_class": {k: round(v[0] / steps * 1e3, 1) for k, v in tm.items() if v[1]}},
+        "hbm_kernels": {"decode_out": {"bytes_per_step": T * O * 8, "us_per_step": round(tm["decode_out"][0] / steps * 1e3, 1),
+                                       "gbs": round(T * O * 8 / (tm["decode_out"][0] / steps * 1e3) / 1e3, 1)}},
+        "clocks": clocks}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c5"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.config == "c5":
+        run_decode(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -1,6 +1,10 @@
 """Data parallel on real GPUs (needs >= 2): K ranks, each feeding its own frames to tfk_accumulate and
-calling tfk_apply (NCCL all-reduce of gradients + loss + frame count inside), must equal ONE GPU
-accumulating the same shards as micro-batches (trainer.py:310-332) — the semantics the reference has."""
+calling tfk_apply, must equal ONE GPU accumulating the same shards as micro-batches
+(trainer.py:310-332) — the semantics the reference has.  Three transports:
+  fused         wgrad epilogue TMA-reduce-adds into the owner GPU's slice over NVLink peer memory,
+                sharded Adam, bf16 all-gather (default on a single node)
+  sharded_nccl  NCCL reduce-scatter instead of the fused epilogue
+  allreduce     NCCL all-reduce, replicated Adam"""
 import os
 import socket
 
@@ -62,7 +66,7 @@ def _worker(rank, world, port, out_dir, mode):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("mode", ["sharded", "allreduce"])
+@pytest.mark.parametrize("mode", ["fused", "sharded_nccl", "allreduce"])
 def test_dp_equals_microbatch_accumulation(cuda_device, tmp_path, mode):
     import torch
     import torch.multiprocessing as mp

@@ -73,6 +73,8 @@ SIGNATURES = [
     ("tfk_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("tfk_comm_init", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
     ("tfk_set_comm", C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    ("tfk_ipc_export", C.c_int, [_H, C.POINTER(C.c_uint8)]),
+    ("tfk_ipc_import", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_int]),
     ("tfk_enable_timers", C.c_int, [_H, C.c_int]),
     ("tfk_get_timers", C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     ("tfk_kernel_launches", C.c_int64, [_H]),

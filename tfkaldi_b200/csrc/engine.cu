@@ -81,6 +81,7 @@ struct Layer {
   bool hidden = false, bn = false;
   size_t off_w = 0, off_b = 0, off_beta = 0;  // offsets (floats) into the parameter arenas
   size_t w_count = 0;                         // floats reserved for W (K*ldn rounded up to 1024)
+  bool peer_reduce = false;                   // wgrad epilogue adds straight into the owner GPU's slice
   float *moving_mean = nullptr, *moving_var = nullptr;  // [npad]
   float *bn_mean = nullptr, *bn_rstd = nullptr;          // statistics used by the last forward
   float* bn_sums = nullptr;                              // [2*ldn] backward column sums
@@ -107,6 +108,9 @@ struct tfk_handle {
   size_t arena_n = 0;
   size_t nW = 0;  // [0, nW): weight regions of all layers; [nW, arena_n): biases and batch-norm betas
   bool sharded = false;       // data parallel with reduce-scatter -> sharded Adam -> all-gather
+  bool fused_rs = false;      // weight-gradient reduce-scatter fused into the wgrad epilogue (peer memory)
+  std::vector<float*> peer_G; // [nranks] every rank's gradient arena (IPC-mapped; own pointer for self)
+  std::vector<void*> ipc_opened;
   bool params_synced = true;  // fp32 master weights / Adam slots identical on every rank
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
   __nv_bfloat16 *Sh = nullptr, *Sl = nullptr;
@@ -249,6 +253,12 @@ int finish_params(tfk_handle* h, Plan& plan, const GemmSpec* s, int n, GemmParam
 void free_plan(Plan& plan) {
   for (int* d : plan.lists) cudaFree(d);
   plan.lists.clear();
+  for (auto& gp : plan.bwd)
+    for (int i = 0; i < 2; ++i)
+      if (gp.p[i].peer_tm) {
+        cudaFree(const_cast<CUtensorMap*>(gp.p[i].peer_tm));
+        gp.p[i].peer_tm = nullptr;
+      }
 }
 
 int build_plan(tfk_handle* h, int B, Plan& plan) {
@@ -311,6 +321,13 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       int ks = (ai > 0 || tiles >= units) ? 1 : (2 * units + tiles - 1) / tiles;
       if (ks > kb / 16) ks = kb / 16;
       s[0].ksplit = ks < 1 ? 1 : ks;
+    }
+    std::vector<void*> peers;
+    if (h->fused_rs && ly.peer_reduce) {  // add each output slab into its owner GPU's accumulator over NVLink
+      for (int r = 0; r < h->nranks; ++r) peers.push_back(h->peer_G[r] + ly.off_w);
+      s[0].peer_D = peers.data();
+      s[0].num_peers = h->nranks;
+      s[0].rows_per_owner = ly.K / h->nranks;
     }
     int nspec = 1;
     if (ai > 0) {
@@ -514,6 +531,7 @@ int reduce_scatter_grads(tfk_handle* h, cudaStream_t st) {
     int rc = api.GroupStart();
     for (int l = h->L; l >= 0 && rc == 0; --l) {
       const Layer& ly = h->layers[l];
+      if (h->fused_rs && ly.peer_reduce) continue;  // already summed into the owners by the wgrad epilogues
       const size_t cnt = ly.w_count / h->nranks;
       rc = api.ReduceScatter(h->G + ly.off_w, h->G + ly.off_w + cnt * h->rank, cnt, kNcclFloat, kNcclSum, h->comm,
                              h->comm_stream);
@@ -654,6 +672,7 @@ int tfk_destroy(tfk_handle* h) {
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   for (auto& kv : h->plans) free_plan(kv.second);
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->allocs) cudaFree(p);
   if (h->acc_host) cudaFreeHost(h->acc_host);
   delete h;
@@ -1050,6 +1069,7 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
     // non-owned gradient slices still hold this rank's local sums: clear them for the next accumulation
     for (int l = 0; l <= h->L; ++l) {
       const Layer& ly = h->layers[l];
+      if (h->fused_rs && ly.peer_reduce) continue;  // non-owned slices were never written locally
       const size_t c = ly.w_count / h->nranks, lo = c * h->rank;
       if (lo) TFK_CUDA(h, cudaMemsetAsync(h->G + ly.off_w, 0, lo * sizeof(float), st));
       if (lo + c < ly.w_count)
@@ -1167,6 +1187,46 @@ int tfk_set_comm(tfk_handle* h, void* nccl_comm, int rank, int nranks) {
   const char* mode = getenv("TFK_DP_MODE");
   h->sharded = h->nranks > 1 && (h->nranks & (h->nranks - 1)) == 0 && h->nranks <= 256 && !(mode && strcmp(mode, "allreduce") == 0);
   return nccl_comm ? setup_comm_streams(h) : TFK_OK;
+}
+
+int tfk_ipc_export(tfk_handle* h, uint8_t* handle64_host) {
+  if (!h || !handle64_host) return fail(h, TFK_EINVAL, "tfk_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaIpcMemHandle_t hd;
+  TFK_CUDA(h, cudaIpcGetMemHandle(&hd, h->G));
+  memcpy(handle64_host, &hd, 64);
+  return TFK_OK;
+}
+
+int tfk_ipc_import(tfk_handle* h, const uint8_t* handles_host, int nranks) {
+  if (!h || !handles_host) return fail(h, TFK_EINVAL, "tfk_ipc_import: null argument");
+  if (!h->sharded || nranks != h->nranks) return fail(h, TFK_EINVAL, "tfk_ipc_import: needs the sharded mode and %d handles", h->nranks);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->peer_G.assign(nranks, nullptr);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == h->rank) { h->peer_G[r] = h->G; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles_host + 64 * r, 64);
+    void* p = nullptr;
+    TFK_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    h->peer_G[r] = static_cast<float*>(p);
+  }
+  // a layer is eligible when its rows split evenly over the ranks in multiples of the 32-row store slab
+  int eligible = 0;
+  for (int l = 0; l <= h->L; ++l) {
+    Layer& ly = h->layers[l];
+    ly.peer_reduce = ly.K % nranks == 0 && (ly.K / nranks) % 32 == 0 &&
+                     ly.w_count == static_cast<size_t>(ly.K) * ly.ldn;
+    eligible += ly.peer_reduce ? 1 : 0;
+  }
+  const char* mode = getenv("TFK_DP_MODE");
+  h->fused_rs = eligible > 0 && !(mode && strcmp(mode, "sharded_nccl") == 0);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->plans) free_plan(kv.second);  // plans built before the import lack the peer maps
+  h->plans.clear();
+  return TFK_OK;
 }
 
 int tfk_enable_timers(tfk_handle* h, int on) {

@@ -235,10 +235,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       __syncwarp();
       if (lane == 0) {
         const uint32_t src = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES;
-        if constexpr (OUT == OUT_F32)
+        if constexpr (OUT == OUT_F32) {
           tma_store_2d(&pr.tmD[0], src, col0, m0 + static_cast<int>(q * 32));
-        else
-          tma_reduce_add_2d(&pr.tmD[0], src, col0, m0 + static_cast<int>(q * 32));
+        } else {
+          // fused reduce-scatter: this 32-row slab belongs to one owner GPU; add it there over NVLink
+          const CUtensorMap* tm = &pr.tmD[0];
+          if (pr.peer_tm != nullptr) {
+            int owner = (m0 + static_cast<int>(q * 32)) / pr.rows_per_owner;
+            owner = owner < pr.num_peers ? owner : pr.num_peers - 1;
+            tm = pr.peer_tm + owner;
+          }
+          tma_reduce_add_2d(tm, src, col0, m0 + static_cast<int>(q * 32));
+        }
         tma_commit_group();
       }
       sbuf ^= 1;
@@ -856,6 +864,31 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.stat_ld = s.stat_ld;
     p.colsum_part = s.colsum_part;
     p.colsum_ld = s.colsum_ld;
+    p.peer_tm = nullptr;
+    p.num_peers = 0;
+    p.rows_per_owner = 0;
+    if (s.peer_D != nullptr && s.num_peers > 1) {
+      if (s.out_kind != OUT_F32_REDADD || s.rows_per_owner <= 0 || s.rows_per_owner % 32 != 0) {
+        snprintf(err, errlen, "gemm: peer reduce needs OUT_F32_REDADD and rows_per_owner %% 32 == 0");
+        return -1;
+      }
+      std::vector<CUtensorMap> maps(s.num_peers);
+      for (int o = 0; o < s.num_peers; ++o) {
+        rc = make_tmap(&maps[o], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s.peer_D[o], s.N, s.M, s.ldd, 32, 32, err, errlen);
+        if (rc) return rc;
+      }
+      CUtensorMap* d = nullptr;
+      cudaError_t ce = cudaMalloc(&d, maps.size() * sizeof(CUtensorMap));
+      if (ce == cudaSuccess) ce = cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) {
+        snprintf(err, errlen, "peer tensor-map upload failed: %s", cudaGetErrorString(ce));
+        if (d) cudaFree(d);
+        return -2;
+      }
+      p.peer_tm = d;
+      p.num_peers = s.num_peers;
+      p.rows_per_owner = s.rows_per_owner;
+    }
     p.tiles_m = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     p.tiles_n = (s.N + BN - 1) / BN;
     p.tile_begin = tile_begin;

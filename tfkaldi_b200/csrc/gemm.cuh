@@ -71,6 +71,12 @@ struct GemmSpec {
   // gradient of the layer below falls out of the dgrad epilogue.  [ceil(M/128)*4, colsum_ld]
   float* colsum_part = nullptr;
   int colsum_ld = 0;
+  // OUT_F32_REDADD only: fused reduce-scatter.  Output rows [o*rows_per_owner, (o+1)*rows_per_owner) are
+  // reduce-added into peer_D[o] (the same [M, ldd] matrix on GPU o, mapped over NVLink; the local pointer
+  // for this rank) instead of D_hi.  rows_per_owner must be a multiple of 32.
+  void* const* peer_D = nullptr;
+  int num_peers = 0;
+  int rows_per_owner = 0;
 };
 
 struct alignas(64) GemmProblem {
@@ -93,6 +99,8 @@ struct alignas(64) GemmProblem {
   int stat_ld;
   float* colsum_part;
   int colsum_ld;
+  const CUtensorMap* peer_tm;  // device array [num_peers] (cudaMalloc'ed by gemm_build_params, freed by the owner)
+  int num_peers, rows_per_owner;
   int tiles_m, tiles_n, tile_begin, num_kb;
   int ksplit, kb_per_split;
 };

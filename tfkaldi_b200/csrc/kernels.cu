@@ -331,16 +331,31 @@ adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups,
-                                   int ld, int N, int rows, float eps, float decay,
-                                   float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ mm, float* __restrict__ mv) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+// block = 32 columns x 8 group lanes; fixed summation order (lane-strided, then lanes 0..7) in double
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups, int ld, int N,
+                   int rows, float eps, float decay, float* __restrict__ mean, float* __restrict__ rstd,
+                   float* __restrict__ mm, float* __restrict__ mv) {
+  __shared__ double sm[2][8][32];
+  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int gidx = 0; gidx < groups; ++gidx) {
-    s1 += static_cast<double>(ps[static_cast<size_t>(gidx) * ld + c]);
-    s2 += static_cast<double>(pq[static_cast<size_t>(gidx) * ld + c]);
+  if (c < N) {
+    for (int gidx = gl; gidx < groups; gidx += 8) {
+      s1 += static_cast<double>(ps[static_cast<size_t>(gidx) * ld + c]);
+      s2 += static_cast<double>(pq[static_cast<size_t>(gidx) * ld + c]);
+    }
+  }
+  sm[0][gl][cl] = s1;
+  sm[1][gl][cl] = s2;
+  __syncthreads();
+  if (gl != 0 || c >= N) return;
+  s1 = 0.0;
+  s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s1 += sm[0][k][cl];
+    s2 += sm[1][k][cl];
   }
   const double mu = s1 / rows;
   double var = s2 / rows - mu * mu;  // biased (no Bessel), as tf.nn.moments
@@ -428,59 +443,52 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
   }
 }
 
-// stage 1 of the BN backward column reductions; ws layout [RS][2][ld]
+// stage 1 of the BN backward column reductions; ws layout [RS][2][ld].  A warp reads 256 consecutive
+// columns (16 B per lane per array) of one row per load; 8 warps stride over the block's row range.
 __global__ void __launch_bounds__(256)
 bn_bwd_stage1_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat16* __restrict__ dy_lo,
                      const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
                      int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
                      float* __restrict__ ws) {
-  __shared__ float sm[2][8][64];
-  const int col = blockIdx.x * 64 + threadIdx.x * 2;
+  __shared__ float sm[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int rs = blockIdx.y;
   const int per = (B + COLSUM_RS - 1) / COLSUM_RS;
   const int r0 = rs * per, r1 = min(B, r0 + per);
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  float a[8], b[8], mu[8], rsd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[k] = 0.f;
+    b[k] = 0.f;
+    mu[k] = (col + k < N) ? mean[col + k] : 0.f;
+    rsd[k] = (col + k < N) ? rstd[col + k] : 0.f;
+  }
   if (col < ld) {
-    const float mu0 = col < N ? mean[col] : 0.f, mu1 = col + 1 < N ? mean[col + 1] : 0.f;
-    const float rs0 = col < N ? rstd[col] : 0.f, rs1 = col + 1 < N ? rstd[col + 1] : 0.f;
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+#pragma unroll 2
+    for (int r = r0 + w; r < r1; r += 8) {
       const size_t o = static_cast<size_t>(r) * ld + col;
-      uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(dy_hi + o));
-      float d0 = bf_lo(w), d1 = bf_hi(w);
-      if (dy_lo) {
-        w = __ldg(reinterpret_cast<const uint32_t*>(dy_lo + o));
-        d0 += bf_lo(w);
-        d1 += bf_hi(w);
+      float d[8], z[8];
+      load8(dy_hi, dy_lo, o, d);
+      load8(z_hi, z_lo, o, z);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[k] += d[k];
+        b[k] += d[k] * ((z[k] - mu[k]) * rsd[k]);
       }
-      w = __ldg(reinterpret_cast<const uint32_t*>(z_hi + o));
-      float z0 = bf_lo(w), z1 = bf_hi(w);
-      if (z_lo) {
-        w = __ldg(reinterpret_cast<const uint32_t*>(z_lo + o));
-        z0 += bf_lo(w);
-        z1 += bf_hi(w);
-      }
-      a0 += d0;
-      a1 += d1;
-      b0 += d0 * ((z0 - mu0) * rs0);
-      b1 += d1 * ((z1 - mu1) * rs1);
     }
   }
-  sm[0][threadIdx.y][threadIdx.x * 2] = a0;
-  sm[0][threadIdx.y][threadIdx.x * 2 + 1] = a1;
-  sm[1][threadIdx.y][threadIdx.x * 2] = b0;
-  sm[1][threadIdx.y][threadIdx.x * 2 + 1] = b1;
-  __syncthreads();
-  if (threadIdx.y < 2) {
-    const int which = threadIdx.y;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int c = threadIdx.x * 2 + k;
-      float s = 0.f;
+  for (int which = 0; which < 2; ++which) {
 #pragma unroll
-      for (int y = 0; y < 8; ++y) s += sm[which][y][c];
-      if (blockIdx.x * 64 + c < ld)
-        ws[(static_cast<size_t>(rs) * 2 + which) * ld + blockIdx.x * 64 + c] = s;
-    }
+    for (int k = 0; k < 8; ++k) sm[w][lane * 8 + k] = which ? b[k] : a[k];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][threadIdx.x];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < ld) ws[(static_cast<size_t>(rs) * 2 + which) * ld + c] = s;
+    __syncthreads();
   }
 }
 __global__ void bn_bwd_stage2_kernel(const float* __restrict__ ws, int ld, int N, float* __restrict__ sums,
@@ -720,7 +728,7 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
 int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int ld, int N, int rows, float eps,
                   float decay, float* mean, float* rstd, float* moving_mean, float* moving_var,
                   cudaStream_t st) {
-  bn_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(part_sum, part_sq, groups, ld, N, rows, eps, decay, mean,
+  bn_finalize_kernel<<<(N + 31) / 32, 256, 0, st>>>(part_sum, part_sq, groups, ld, N, rows, eps, decay, mean,
                                                      rstd, moving_mean, moving_var);
   return static_cast<int>(cudaGetLastError());
 }
@@ -742,8 +750,8 @@ int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
                     float* ws, float* sums, float* g_beta, cudaStream_t st) {
-  dim3 grid((ld + 63) / 64, COLSUM_RS), block(32, 8);
-  bn_bwd_stage1_kernel<<<grid, block, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws);
+  dim3 grid((ld + 255) / 256, COLSUM_RS);
+  bn_bwd_stage1_kernel<<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws);
   bn_bwd_stage2_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, ld, N, sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }

@@ -3,6 +3,7 @@ host buffers only; all arithmetic runs in libtfkaldi_b200.so (hand-written sm_10
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -213,6 +214,16 @@ class Engine:
         dist.broadcast_object_list(payload, src=0)
         ident = (C.c_uint8 * 128).from_buffer_copy(payload[0])
         self._check(self.lib.tfk_comm_init(self.h, ident, rank, world))
+        mode = os.environ.get("TFK_DP_MODE", "")
+        if mode not in ("allreduce", "sharded_nccl") and world & (world - 1) == 0:
+            # single-node peer memory: let the wgrad epilogues reduce-add into the owners' accumulators
+            mine = (C.c_uint8 * 64)()
+            self._check(self.lib.tfk_ipc_export(self.h, mine))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(mine))
+            blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+            self._check(self.lib.tfk_ipc_import(self.h, blob, world))
+            dist.barrier()
 
     # ------------------------------------------------------------------ measurement
     def enable_timers(self, on=True):
