@@ -40,6 +40,8 @@ extern "C" {
 /* hidden-layer non-linearity (reference: neuralNetworks/nnet.py:47-65) */
 #define TFK_NONLIN_RELU 0
 #define TFK_NONLIN_LINEAR 1
+#define TFK_NONLIN_SIGMOID 2
+#define TFK_NONLIN_TANH 3
 
 /* tensor kinds for tfk_set_tensor / tfk_get_tensor.  `layer` = 0..L-1 hidden, L = output layer.
  * Names in comments are the reference's TF variable names. */
@@ -85,6 +87,8 @@ typedef struct tfk_config {
   int32_t precision;    /* TFK_PREC_* */
   int32_t device;       /* CUDA device ordinal */
   uint64_t seed;        /* dropout Philox key base */
+  int32_t l2_norm;      /* 0/1: L2Norm after the nonlinearity (nnet.py:67-68, activation.py:87-111) */
+  int32_t reserved;
 } tfk_config;
 
 /* Fill `cfg` with the reference's defaults (ReLU, no BN, keep 1, Adam/BN TF defaults, bf16). */

@@ -51,8 +51,9 @@ class OracleConfig:
     input_dim: int  # spliced feature dimension   nnet.py:40
     hidden_dim: int
     output_dim: int
-    nonlin: str = "relu"  # 'relu' | 'linear'           nnet.py:47-62
+    nonlin: str = "relu"  # 'relu' | 'sigmoid' | 'tanh' | 'linear'   nnet.py:47-62
     batch_norm: bool = False  # nnet.py:42
+    l2_norm: bool = False  # nnet.py:67-68
     keep_prob: float = 1.0  # conf['dropout'] = KEEP prob nnet.py:70-72, activation.py:141
     bn_eps: float = 1e-3  # tf.contrib.layers.batch_norm defaults (App. A.3)
     bn_decay: float = 0.999
@@ -91,6 +92,9 @@ class _LayerCache:
     xhat: np.ndarray | None = None
     rstd: np.ndarray | None = None
     y: np.ndarray | None = None  # output after the whole activation chain
+    a: np.ndarray | None = None  # output of the nonlinearity (before dropout)
+    keep: np.ndarray | None = None  # dropout keep mask (training with keep_prob < 1)
+    sig: np.ndarray | None = None  # L2Norm: per-frame mean square of a
 
 
 class OracleDNN:
@@ -117,6 +121,10 @@ class OracleDNN:
             return np.maximum(a, F32(0))
         if self.cfg.nonlin == "linear":
             return a
+        if self.cfg.nonlin == "sigmoid":
+            return (F32(1) / (F32(1) + np.exp(-a))).astype(F32, copy=False)
+        if self.cfg.nonlin == "tanh":
+            return np.tanh(a).astype(F32, copy=False)
         raise Exception("unkown nonlinearity")  # nnet.py:65 (sic)
 
     def forward(self, x: np.ndarray, training: bool, dropout_seed: int = 0):
@@ -150,10 +158,16 @@ class OracleDNN:
             else:
                 h = z
             h = self._nonlin(h)
+            c.a = h
+            if cfg.l2_norm:
+                # L2Norm._apply_func (classifiers/activation.py:103-111): sig = mean over columns of a^2;
+                # a / sig where sig > 1, else a  (the mean SQUARE, not its root - reference quirk kept)
+                c.sig = np.mean(np.square(h, dtype=np.float64), axis=1, keepdims=True).astype(F32)
+                h = np.where(c.sig > 1, h / c.sig, h).astype(F32, copy=False)
             if training and cfg.keep_prob < 1.0:
                 # tf.nn.dropout: x / keep * floor(keep + u)   classifiers/activation.py:140-141
-                keep = dropout_keep_mask(dropout_seed + l, h.shape[0], h.shape[1], cfg.keep_prob)
-                h = np.where(keep, h * F32(1.0 / cfg.keep_prob), F32(0)).astype(F32, copy=False)
+                c.keep = dropout_keep_mask(dropout_seed + l, h.shape[0], h.shape[1], cfg.keep_prob)
+                h = np.where(c.keep, h * F32(1.0 / cfg.keep_prob), F32(0)).astype(F32, copy=False)
             c.y = h.astype(F32, copy=False)
             caches.append(c)
             a = c.y
@@ -196,19 +210,22 @@ class OracleDNN:
         da = _mm(dlogits, self.p[f"W{L}"].T).astype(F32, copy=False)
         for l in range(self.active - 1, -1, -1):
             c = caches[l]
-            # dropout + nonlinearity backward.  With y = nonlin(h)/keep*mask: relu passes where y > 0
-            # (mask=0 or relu'=0 both give y == 0); linear passes where the dropout mask kept the unit.
-            if cfg.nonlin == "relu":
-                passed = c.y > 0
-            elif cfg.keep_prob < 1.0:
-                passed = c.y != 0
-            else:
-                passed = None
+            # dropout backward, then the nonlinearity's slope at its own output a = f(h)
             dh = da
-            if cfg.keep_prob < 1.0:
-                dh = dh * F32(1.0 / cfg.keep_prob)
-            if passed is not None:
-                dh = np.multiply(dh, passed, dtype=F32)  # zero where the unit did not pass
+            if c.keep is not None:
+                dh = np.multiply(dh * F32(1.0 / cfg.keep_prob), c.keep, dtype=F32)
+            if cfg.l2_norm:
+                # y = a / sig(a): dy/da = I/sig - a (2a/N)^T / sig^2 on the normalised rows, identity elsewhere
+                n = F32(c.a.shape[1])
+                dot = np.sum(dh * c.a, axis=1, keepdims=True, dtype=np.float64).astype(F32)
+                dn = dh / c.sig - c.a * (F32(2) * dot / (n * c.sig * c.sig))
+                dh = np.where(c.sig > 1, dn, dh).astype(F32, copy=False)
+            if cfg.nonlin == "relu":
+                dh = np.multiply(dh, c.a > 0, dtype=F32)
+            elif cfg.nonlin == "sigmoid":
+                dh = (dh * (c.a * (F32(1) - c.a))).astype(F32, copy=False)
+            elif cfg.nonlin == "tanh":
+                dh = (dh * (F32(1) - c.a * c.a)).astype(F32, copy=False)
             if cfg.batch_norm:
                 # y = xhat + beta: dbeta = sum dy; dz = r * (dy - mean(dy) - xhat * mean(dy*xhat))  (App. A.3)
                 g[f"beta{l}"] = dh.sum(axis=0, dtype=F32)

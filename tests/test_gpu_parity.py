@@ -56,7 +56,7 @@ def make_pair(cfg: OracleConfig, max_frames, precision, seed=0, random_out=False
             for l in range(L):
                 params[f"beta{l}"] = (0.1 * rng.standard_normal(cfg.hidden_dim)).astype(np.float32)
     eng = Engine(cfg.num_layers, cfg.input_dim, cfg.hidden_dim, cfg.output_dim, max_frames, nonlin=cfg.nonlin,
-                 batch_norm=cfg.batch_norm, keep_prob=cfg.keep_prob, precision=precision, seed=1000)
+                 batch_norm=cfg.batch_norm, keep_prob=cfg.keep_prob, precision=precision, seed=1000, l2_norm=cfg.l2_norm)
     eng.load_params(params)
     return OracleDNN(cfg, params), eng, rng
 
@@ -69,6 +69,11 @@ VARIANTS = {
     "bn_dropout": dict(batch_norm=True, keep_prob=0.5),
     "linear": dict(nonlin="linear"),
     "linear_bn_dropout": dict(nonlin="linear", batch_norm=True, keep_prob=0.7),
+    "sigmoid": dict(nonlin="sigmoid"),
+    "tanh_dropout": dict(nonlin="tanh", keep_prob=0.8),
+    "bn_sigmoid_dropout": dict(nonlin="sigmoid", batch_norm=True, keep_prob=0.6),
+    "relu_l2norm_dropout": dict(l2_norm=True, keep_prob=0.5),  # the chain of config_CGN.cfg
+    "linear_bn_l2norm": dict(nonlin="linear", batch_norm=True, l2_norm=True),
 }
 
 
@@ -135,6 +140,8 @@ def test_single_step_gradients(cuda_device, variant):
     orc, eng, rng = make_pair(cfg, 300, "bf16x3", seed=11, random_out=True)
     B = 300  # not a multiple of the 128-row tile
     x = rng.standard_normal((B, 440)).astype(np.float32)
+    if cfg.l2_norm:
+        x[::2] *= 3  # drive some frames above mean square 1: both L2Norm branches
     y = rng.integers(0, 183, B)
     y[5] = 183  # out-of-range label: empty one-hot row (tf.one_hot) -> no loss, no gradient
     eng.set_dropout_seed(77)
@@ -143,7 +150,7 @@ def test_single_step_gradients(cuda_device, variant):
     assert abs(eng.get_scalar(L.S_LOSS_SUM) - orc.loss_sum) <= TOL * orc.loss_sum
     assert eng.get_scalar(L.S_NUM_FRAMES) == B
     kinds = {"W": L.T_GRAD_W, "b": L.T_GRAD_B, "beta": L.T_GRAD_BETA}
-    strict = cfg.nonlin == "linear"
+    strict = cfg.nonlin != "relu"  # smooth / linear chains have no discontinuity
     for k, want in orc.grads.items():
         if is_bn_bias(cfg, k):
             continue  # exactly 0 in exact arithmetic: pure round-off on both sides
@@ -184,7 +191,7 @@ def test_adam_kernel_exact_on_injected_gradients(cuda_device):
     assert eng.get_scalar(L.S_GLOBAL_STEP) == 3 and eng.get_scalar(L.S_NUM_FRAMES) == 0
 
 
-@pytest.mark.parametrize("variant", ["linear", "plain", "bn_dropout"])
+@pytest.mark.parametrize("variant", ["linear", "plain", "bn_dropout", "tanh_dropout"])
 def test_c1_training_trajectory(cuda_device, variant):
     """Config C1 (440-256-256-183, 256-frame micro-batches, 2 per step), 20 optimizer steps from the
     reference's initialisation.  Loss trajectory <= 1e-3 at every step; final weights and the
@@ -204,7 +211,7 @@ def test_c1_training_trajectory(cuda_device, variant):
             seed += 3
         worst = max(worst, close(eng.apply(1e-3), orc.apply(1e-3)))
     assert worst < TOL, f"loss trajectory deviates {worst}"
-    strict = variant == "linear"
+    strict = cfg.nonlin != "relu"
     got = eng.dump_params()
     for k, want in orc.p.items():
         if is_bn_bias(cfg, k):

@@ -134,6 +134,13 @@ def torch_model_grads(cfg, params, x, y, keep_masks):
             z = (z - mu) / torch.sqrt(var + cfg.bn_eps) + P[f"beta{l}"]
         if cfg.nonlin == "relu":
             z = torch.relu(z)
+        elif cfg.nonlin == "sigmoid":
+            z = torch.sigmoid(z)
+        elif cfg.nonlin == "tanh":
+            z = torch.tanh(z)
+        if cfg.l2_norm:
+            sig = (z ** 2).mean(1, keepdim=True)
+            z = torch.where(sig > 1, z / sig, z)
         if cfg.keep_prob < 1:
             z = z / cfg.keep_prob * torch.tensor(keep_masks[l], dtype=torch.float64)
         a = z
@@ -143,16 +150,29 @@ def torch_model_grads(cfg, params, x, y, keep_masks):
     return float(loss.detach()), {k: v.grad.numpy() for k, v in P.items() if v.requires_grad}, logits.detach().numpy()
 
 
+def test_l2norm_by_hand():
+    """row [3, 0, -4, 0] -> mean square 6.25 > 1 -> row / 6.25 ; row [0.5, 0.5, 0, 0] -> 0.125 <= 1 -> unchanged"""
+    cfg = OracleConfig(num_layers=1, input_dim=4, hidden_dim=4, output_dim=2, nonlin="linear", l2_norm=True)
+    p = {"W0": np.eye(4), "b0": np.zeros(4), "W1": np.zeros((4, 2)), "b1": np.zeros(2)}
+    o = OracleDNN(cfg, p)
+    _, caches = o.forward(np.array([[3, 0, -4, 0], [0.5, 0.5, 0, 0]], np.float32), training=False)
+    assert np.allclose(caches[0].y, [[0.48, 0, -0.64, 0], [0.5, 0.5, 0, 0]], atol=1e-7)
+
+
 @pytest.mark.parametrize("bn,keep,nonlin", [(False, 1.0, "relu"), (True, 1.0, "relu"), (False, 0.5, "relu"),
-                                            (True, 0.5, "relu"), (False, 0.7, "linear"), (True, 1.0, "linear")])
-def test_explicit_backward_matches_float64_autograd(bn, keep, nonlin):
-    cfg = OracleConfig(num_layers=3, input_dim=24, hidden_dim=40, output_dim=11, batch_norm=bn, keep_prob=keep, nonlin=nonlin)
+                                            (True, 0.5, "relu"), (False, 0.7, "linear"), (True, 1.0, "linear"),
+                                            (False, 1.0, "sigmoid"), (True, 0.6, "sigmoid"), (False, 0.8, "tanh"), (True, 1.0, "tanh")])
+@pytest.mark.parametrize("l2", [False, True])
+def test_explicit_backward_matches_float64_autograd(bn, keep, nonlin, l2):
+    cfg = OracleConfig(num_layers=3, input_dim=24, hidden_dim=40, output_dim=11, batch_norm=bn, keep_prob=keep, nonlin=nonlin, l2_norm=l2)
     rng = np.random.default_rng(7)
     params = reference_init(cfg, rng)
     params["W3"] = (rng.standard_normal((40, 11)) / math.sqrt(40)).astype(np.float32)
     for l in range(4):
         params[f"b{l}"] = (0.1 * rng.standard_normal(params[f"b{l}"].shape)).astype(np.float32)
     x, y = rng.standard_normal((64, 24)).astype(np.float32), rng.integers(0, 11, 64)
+    if l2:
+        x[::2] *= 4  # make some frames exceed mean square 1 so both L2Norm branches are taken
     o = OracleDNN(cfg, params)
     seed = 99
     loss = o.accumulate(x, y, dropout_seed=seed)

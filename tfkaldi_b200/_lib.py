@@ -15,7 +15,7 @@ TFK_OK = 0
 TFK_EINVAL, TFK_ECUDA, TFK_ENCCL, TFK_ESHAPE = -1, -2, -3, -4
 TFK_ABI_VERSION = 1
 TFK_PREC_BF16, TFK_PREC_BF16X3 = 0, 1
-TFK_NONLIN_RELU, TFK_NONLIN_LINEAR = 0, 1
+TFK_NONLIN_RELU, TFK_NONLIN_LINEAR, TFK_NONLIN_SIGMOID, TFK_NONLIN_TANH = 0, 1, 2, 3
 
 (T_WEIGHTS, T_BIASES, T_BN_BETA, T_BN_MOVING_MEAN, T_BN_MOVING_VAR, T_ADAM_M_W, T_ADAM_V_W, T_ADAM_M_B,
  T_ADAM_V_B, T_ADAM_M_BETA, T_ADAM_V_BETA, T_GRAD_W, T_GRAD_B, T_GRAD_BETA) = range(14)
@@ -43,6 +43,8 @@ class TfkConfig(C.Structure):
         ("precision", C.c_int32),
         ("device", C.c_int32),
         ("seed", C.c_uint64),
+        ("l2_norm", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

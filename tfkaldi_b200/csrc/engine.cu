@@ -86,6 +86,8 @@ struct Layer {
   float *bn_mean = nullptr, *bn_rstd = nullptr;          // statistics used by the last forward
   float* bn_sums = nullptr;                              // [2*ldn] backward column sums
   __nv_bfloat16 *z_hi = nullptr, *z_lo = nullptr;        // pre-BN linear output [maxB, ldn]
+  __nv_bfloat16 *u_hi = nullptr, *u_lo = nullptr;        // L2Norm: output of the nonlinearity [maxB, ldn]
+  float* l2_s = nullptr;                                 // L2Norm: per-frame mean square [maxB]
   uint32_t* maskbits = nullptr;  // [ceil(ldn/32), maxB] gradient-pass bits written by the forward epilogue
   float* db_part = nullptr;  // [maxB/32 + 8, ldn] bias-gradient partials written by the dgrad epilogue above
 };
@@ -264,7 +266,10 @@ void free_plan(Plan& plan) {
 int build_plan(tfk_handle* h, int B, Plan& plan) {
   const int L = h->L, act = h->active;
   const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU;
+  const bool smooth = h->cfg.nonlin == TFK_NONLIN_SIGMOID || h->cfg.nonlin == TFK_NONLIN_TANH;
+  const int act_code = relu ? 1 : h->cfg.nonlin == TFK_NONLIN_SIGMOID ? 2 : h->cfg.nonlin == TFK_NONLIN_TANH ? 3 : 0;
   const bool drop = h->cfg.keep_prob < 1.0f;
+  const bool l2 = h->cfg.l2_norm != 0;
   plan.fwd_train.assign(L + 1, GemmParams());
   plan.fwd_eval.assign(L + 1, GemmParams());
   plan.bwd.assign(L + 1, GemmParams());
@@ -289,9 +294,12 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       } else {
         s.out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
         s.D_hi = h->act_hi[l + 1]; s.D_lo = h->act_lo[l + 1]; s.ldd = ly.ldn;
-        s.relu = relu;
-        if (train && drop) { s.keep = h->cfg.keep_prob; s.seed = 0; }
-        if (train && (relu || drop)) {
+        s.act = act_code;
+        if (l2) {  // the L2Norm kernel finishes the chain (normalise + dropout) from u
+          s.D_hi = ly.u_hi; s.D_lo = ly.u_lo;
+        }
+        if (!l2 && train && drop) { s.keep = h->cfg.keep_prob; s.seed = 0; }
+        if (!l2 && train && !smooth && (relu || drop)) {
           s.mask_bits_out = ly.maskbits; s.mask_bits_ld = h->cfg.max_frames; s.mask_nonzero = relu ? 0 : 1;
         }
       }
@@ -340,7 +348,17 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       s[1].B_hi = h->Sh + ly.off_w; s[1].B_lo = opt(h->Sl, ly.off_w); s[1].ldb = ly.ldn; s[1].b_mn = 0;
       s[1].out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
       s[1].D_hi = h->dA_hi[dst]; s[1].D_lo = h->dA_lo[dst]; s[1].ldd = h->layers[lower].ldn;
-      if (relu || drop) {
+      if (l2) {  // the layer below ends in L2Norm: only its dropout is undone here, the rest in k_l2norm_bwd
+        if (drop) {
+          s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
+          s[1].mask_nonzero = 1; s[1].scale = 1.0f / h->cfg.keep_prob;
+        }
+      } else if (smooth) {  // sigmoid / tanh: slope from the stored forward output
+        s[1].mask_src = h->act_hi[ai]; s[1].mask_src_lo = h->act_lo[ai]; s[1].mask_ld = h->layers[lower].ldn;
+        s[1].deriv = h->cfg.nonlin == TFK_NONLIN_SIGMOID ? 1 : 2;
+        s[1].dropout_in_chain = drop ? 1 : 0;
+        s[1].scale = drop ? 1.0f / h->cfg.keep_prob : 1.0f;
+      } else if (relu || drop) {
         if (h->layers[lower].bn) {  // activation written by bn_apply: test the stored forward output
           s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
         } else {                    // 1 bit per unit, written by the forward epilogue
@@ -349,7 +367,7 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
         s[1].mask_nonzero = relu ? 0 : 1;
         s[1].scale = drop ? 1.0f / h->cfg.keep_prob : 1.0f;
       }
-      if (!h->layers[lower].bn) {  // dz of the layer below is final here: take its column sums for free
+      if (!h->layers[lower].bn && !l2) {  // dz of the layer below is final here: take its column sums for free
         s[1].colsum_part = h->layers[lower].db_part;
         s[1].colsum_ld = h->layers[lower].ldn;
       }
@@ -391,7 +409,8 @@ int check_frames(tfk_handle* h, int B, const char* what) {
 int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bool with_output,
                   cudaStream_t st) {
   const int L = h->L;
-  const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU;
+  const int act_code = h->cfg.nonlin == TFK_NONLIN_RELU ? 1 : h->cfg.nonlin == TFK_NONLIN_SIGMOID ? 2
+                       : h->cfg.nonlin == TFK_NONLIN_TANH ? 3 : 0;
   for (int l = first; l <= L; ++l) {
     if (l < L && l >= h->active) continue;
     if (l == L && !with_output) break;
@@ -411,10 +430,17 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
         TFK_LAUNCH(h, k_bn_eval_stats(ly.moving_mean, ly.moving_var, ly.N, h->cfg.bn_eps, ly.bn_mean,
                                       ly.bn_rstd, st));
       }
-      const float keep = (training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
+      const bool l2 = h->cfg.l2_norm != 0;
+      const float keep = (!l2 && training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
       TFK_LAUNCH(h, k_bn_apply(ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd, h->P + ly.off_beta,
-                               relu ? 1 : 0, keep, h->drop_seed + static_cast<unsigned long long>(l),
-                               h->act_hi[l + 1], h->act_lo[l + 1], st));
+                               act_code, keep, h->drop_seed + static_cast<unsigned long long>(l),
+                               l2 ? ly.u_hi : h->act_hi[l + 1], l2 ? ly.u_lo : h->act_lo[l + 1], st));
+    }
+    if (ly.hidden && h->cfg.l2_norm) {
+      TimerScope ts(h, st, TFK_TIMER_BN);
+      const float keep = (training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
+      TFK_LAUNCH(h, k_l2norm_fwd(ly.u_hi, ly.u_lo, ly.ldn, B, ly.N, keep, h->drop_seed + static_cast<unsigned long long>(l),
+                                 h->act_hi[l + 1], h->act_lo[l + 1], ly.l2_s, st));
     }
   }
   return TFK_OK;
@@ -428,6 +454,12 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
   __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
   __nv_bfloat16* dz_lo = ly.hidden ? h->dA_lo[(L - 1 - l) & 1] : h->dzo_lo;
   const int ldz = ly.hidden ? ly.ldn : h->ldo;
+  if (ly.hidden && h->cfg.l2_norm) {  // d(L2Norm output) -> d(pre-nonlinearity)
+    TimerScope ts(h, st, TFK_TIMER_BN);
+    const int act_code = h->cfg.nonlin == TFK_NONLIN_RELU ? 1 : h->cfg.nonlin == TFK_NONLIN_SIGMOID ? 2
+                         : h->cfg.nonlin == TFK_NONLIN_TANH ? 3 : 0;
+    TFK_LAUNCH(h, k_l2norm_bwd(dz_hi, dz_lo, ly.u_hi, ly.u_lo, ly.l2_s, ly.ldn, B, ly.N, act_code, st));
+  }
   if (ly.hidden && ly.bn) {  // d(bn output) -> d(linear output), plus dbeta
     TimerScope ts(h, st, TFK_TIMER_BN, 3);
     TFK_LAUNCH(h, k_bn_bwd_reduce(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
@@ -435,7 +467,7 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
     TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
                                  ly.bn_sums, st));
   }
-  if (!fused_colsum || !ly.hidden || ly.bn) {
+  if (!fused_colsum || !ly.hidden || ly.bn || h->cfg.l2_norm) {
     TimerScope ts(h, st, TFK_TIMER_COLSUM);
     TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws_colsum, h->G + ly.off_b, st));
   }
@@ -609,7 +641,7 @@ int ce_and_backward(tfk_handle* h, Plan& plan, const int32_t* labels, int B, boo
     float* outs[64];
     int n = 0;
     for (int l = 0; l < h->active; ++l)
-      if (!h->layers[l].bn) {
+      if (!h->layers[l].bn && !h->cfg.l2_norm) {
         parts[n] = h->layers[l].db_part;
         outs[n] = h->G + h->layers[l].off_b;
         ++n;
@@ -690,7 +722,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
                 cfg->input_dim, cfg->hidden_dim, cfg->output_dim, cfg->max_frames);
   if (!(cfg->keep_prob > 0.0f))
     return fail(nullptr, TFK_EINVAL, "tfk_create: keep_prob must be in (0,1] (classifiers/activation.py:127)");
-  if (cfg->nonlin != TFK_NONLIN_RELU && cfg->nonlin != TFK_NONLIN_LINEAR)
+  if (cfg->nonlin < TFK_NONLIN_RELU || cfg->nonlin > TFK_NONLIN_TANH)
     return fail(nullptr, TFK_EINVAL, "tfk_create: unknown nonlinearity %d (nnet.py:65)", cfg->nonlin);
   if (cfg->precision != TFK_PREC_BF16 && cfg->precision != TFK_PREC_BF16X3)
     return fail(nullptr, TFK_EINVAL, "tfk_create: unknown precision %d", cfg->precision);
@@ -774,6 +806,14 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     const size_t n = static_cast<size_t>(maxB) * (l == 0 ? h->ld0 : h->ldh);
     CREATE_TRY(dev_alloc(h, &h->act_hi[l], n));
     if (h->x3) CREATE_TRY(dev_alloc(h, &h->act_lo[l], n));
+  }
+  if (cfg->l2_norm) {
+    for (int l = 0; l < L; ++l) {
+      Layer& ly = h->layers[l];
+      CREATE_TRY(dev_alloc(h, &ly.u_hi, static_cast<size_t>(maxB) * ly.ldn));
+      if (h->x3) CREATE_TRY(dev_alloc(h, &ly.u_lo, static_cast<size_t>(maxB) * ly.ldn));
+      CREATE_TRY(dev_alloc(h, &ly.l2_s, maxB));
+    }
   }
   for (int l = 0; l < L; ++l) {
     if (!h->layers[l].bn) {
@@ -906,6 +946,7 @@ int tfk_fflayer_fwd(tfk_handle* h, int layer, const float* x, float* y, int B, i
   if (!h || !x || !y) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: null argument");
   if (layer < 0 || layer > h->L) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: layer %d", layer);
   if (layer < h->L && layer >= h->active) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: layer %d is not active", layer);
+  if (h->cfg.l2_norm && layer < h->L) return fail(h, TFK_EINVAL, "tfk_fflayer_fwd: per-layer entry points do not cover L2Norm chains");
   TFK_TRY(check_frames(h, B, "tfk_fflayer_fwd"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -940,6 +981,7 @@ int tfk_fflayer_bwd(tfk_handle* h, int layer, const float* dy, float* dx, int B,
   if (!h || !dy) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: null argument");
   if (layer < 0 || layer > h->L) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: layer %d", layer);
   if (layer < h->L && layer >= h->active) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: layer %d is not active", layer);
+  if (h->cfg.l2_norm && layer < h->L) return fail(h, TFK_EINVAL, "tfk_fflayer_bwd: per-layer entry points do not cover L2Norm chains");
   TFK_TRY(check_frames(h, B, "tfk_fflayer_bwd"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -957,10 +999,12 @@ int tfk_fflayer_bwd(tfk_handle* h, int layer, const float* dy, float* dx, int B,
     TimerScope ts(h, st, TFK_TIMER_CONVERT, 3);
     const float* src = dy;
     const bool relu = h->cfg.nonlin == TFK_NONLIN_RELU, drop = h->cfg.keep_prob < 1.0f;
-    if (ly.hidden && (relu || drop)) {
+    const bool smooth = h->cfg.nonlin == TFK_NONLIN_SIGMOID || h->cfg.nonlin == TFK_NONLIN_TANH;
+    if (ly.hidden && (relu || drop || smooth)) {
       TFK_LAUNCH(h, k_merge_bf16(h->act_hi[layer + 1], h->act_lo[layer + 1], ly.ldn, h->tmp_f32, ly.N, B, ly.N, st));
       TFK_LAUNCH(h, k_mask_scale_f32(dy, h->tmp_f32, h->tmp_f32, static_cast<size_t>(B) * ly.N,
-                                     drop ? 1.0f / h->cfg.keep_prob : 1.0f, relu ? 0 : 1, st));
+                                     drop ? 1.0f / h->cfg.keep_prob : 1.0f,
+                                     (relu ? 0 : h->cfg.nonlin == TFK_NONLIN_SIGMOID ? 2 : h->cfg.nonlin == TFK_NONLIN_TANH ? 3 : 1) | (drop ? 4 : 0), st));
       src = h->tmp_f32;
     }
     TFK_LAUNCH(h, k_split_f32(src, ly.N, dz_hi, h->x3 ? dz_lo : nullptr, ldz, B, ly.N, st));

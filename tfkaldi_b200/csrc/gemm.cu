@@ -153,9 +153,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         pr.stat_sq[o] = t2;
       }
     }
-    if (pr.relu) {
+    if (pr.act == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (pr.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+    } else if (pr.act == 3) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
     }
     if (pr.drop_thr != 0u) {
 #pragma unroll
@@ -183,6 +189,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * pr.scale : 0.f;
     }
+    if (pr.mask_src != nullptr && pr.deriv != 0) {
+      // backward of sigmoid / tanh (+dropout) from the stored forward output a = f(z) * dropmask / keep
+      const float keep = 1.0f / pr.scale;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool ok = row_ok && (col0 + j) < pr.N;
+        const size_t o = static_cast<size_t>(row) * pr.mask_ld + col0 + j;
+        float a = ok ? __bfloat162float(pr.mask_src[o]) : 0.f;
+        if (ok && pr.mask_src_lo != nullptr) a += __bfloat162float(pr.mask_src_lo[o]);
+        const float y = a * keep;
+        const float d = pr.deriv == 1 ? y * (1.0f - y) : 1.0f - y * y;
+        const bool dropped = pr.dropout_in_chain && a == 0.f;
+        v[j] = (ok && !dropped) ? v[j] * d * pr.scale : 0.f;
+      }
+    } else
     if (pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
       const __nv_bfloat16* mp = pr.mask_src + static_cast<size_t>(row) * pr.mask_ld + col0;
       if (row_ok && col0 + 32 <= pr.N) {
@@ -847,7 +868,10 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.b_mn = s.b_mn;
     p.nsplit = s.nsplit;
     p.out_kind = s.out_kind;
-    p.relu = s.relu;
+    p.act = s.act;
+    p.deriv = s.deriv;
+    p.mask_src_lo = s.mask_src_lo;
+    p.dropout_in_chain = s.dropout_in_chain;
     p.mask_ld = s.mask_ld;
     p.mask_nonzero = s.mask_nonzero;
     p.mask_bits_out = s.mask_bits_out;

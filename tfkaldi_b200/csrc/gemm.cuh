@@ -49,9 +49,14 @@ struct GemmSpec {
   void* D_lo = nullptr;
   int ldd = 0;
   const float* bias = nullptr;  // [>= roundup(N,256)] added per column, or null
-  int relu = 0;
+  int act = 0;  // element-wise nonlinearity after bias: 0 none, 1 relu, 2 sigmoid, 3 tanh (nnet.py:47-62)
   const __nv_bfloat16* mask_src = nullptr;  // [M, mask_ld]: v = pass(mask_src) ? v*scale : 0
+  const __nv_bfloat16* mask_src_lo = nullptr;  // optional low half (bf16x3 storage), used by deriv != 0
   int mask_ld = 0;
+  // deriv != 0: mask_src holds the stored activation a = f(z) * dropmask / keep and the epilogue multiplies by
+  // f'(z) * dropmask / keep reconstructed from it: 1 sigmoid y(1-y), 2 tanh 1-y^2, y = a / scale... (scale = 1/keep)
+  int deriv = 0;
+  int dropout_in_chain = 0;  // deriv == 2 only: a == 0 means "dropped" (otherwise tanh(0) = 0 keeps slope 1)
   int mask_nonzero = 0;  // 0: pass where mask_src > 0 (relu);  1: pass where mask_src != 0 (linear+dropout)
   float scale = 1.0f;
   // Compact alternative to mask_src: 1 bit per element, word (col/32, row) at bits[(col/32)*mask_bits_ld + row]
@@ -85,11 +90,13 @@ struct alignas(64) GemmProblem {
   CUtensorMap tmD[2];
   int M, N, K;
   int a_mn, b_mn, nsplit, out_kind;
-  int relu, mask_ld, mask_nonzero;
+  int act, mask_ld, mask_nonzero, deriv;
   float scale, keep_inv;
   unsigned int drop_thr;  // keep element iff (philox >> 8) >= drop_thr; 0 => no dropout
   const float* bias;
   const __nv_bfloat16* mask_src;
+  const __nv_bfloat16* mask_src_lo;
+  int dropout_in_chain;
   uint32_t* mask_bits_out;
   const uint32_t* mask_bits_in;
   int mask_bits_ld;

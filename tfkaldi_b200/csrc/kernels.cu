@@ -76,12 +76,23 @@ __global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __
 }
 
 __global__ void mask_scale_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                                      float* __restrict__ out, size_t n, float scale, int nonzero) {
+                                      float* __restrict__ out, size_t n, float scale, int mode) {
+  // mode 0: pass where y > 0; 1: pass where y != 0; 2: sigmoid; 3: tanh; +4: dropout in the chain (y == 0 => dropped)
+  const int kind = mode & 3;
+  const bool drop = (mode & 4) != 0;
+  const float keep = 1.0f / scale;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float yy = y[i];
-    const bool pass = nonzero ? (yy != 0.f) : (yy > 0.f);
-    out[i] = pass ? dy[i] * scale : 0.f;
+    const float a = y[i];
+    float f;
+    if (kind == 0) f = a > 0.f ? scale : 0.f;
+    else if (kind == 1) f = a != 0.f ? scale : 0.f;
+    else {
+      const float yy = a * keep;
+      const float d = kind == 2 ? yy * (1.0f - yy) : 1.0f - yy * yy;
+      f = (drop && a == 0.f) ? 0.f : d * scale;
+    }
+    out[i] = dy[i] * f;
   }
 }
 __global__ void double_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst) {
@@ -424,7 +435,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
       float y = 0.f;
       if (col < N) {
         y = (x[k] - mean[col]) * rstd[col] + beta[col];
-        if (relu) y = fmaxf(y, 0.f);
+        if (relu == 1) y = fmaxf(y, 0.f);
+        else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
+        else if (relu == 3) y = tanhf(y);
       }
       x[k] = y;
     }
@@ -536,6 +549,85 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// L2Norm: one warp per frame, the row is walked twice (second pass hits L1/L2); 8 columns per lane per step.
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ u_hi, const __nv_bfloat16* __restrict__ u_lo, int ld, int B,
+                  int N, unsigned int drop_thr, float keep_inv, unsigned long long seed,
+                  __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, float* __restrict__ s_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const size_t base = static_cast<size_t>(row) * ld;
+  float ss = 0.f;
+  for (int c = lane * 8; c < ld; c += 256) {
+    float x[8];
+    load8(u_hi, u_lo, base + c, x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss += (c + k < N) ? x[k] * x[k] : 0.f;
+  }
+  ss = warp_sum(ss);
+  const float sig = ss / static_cast<float>(N);  // reduce_mean(square(activations), 1)
+  if (lane == 0) s_out[row] = sig;
+  const bool norm = sig > 1.0f;
+  for (int c = lane * 8; c < ld; c += 256) {
+    float x[8];
+    load8(u_hi, u_lo, base + c, x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (c + k < N) ? (norm ? x[k] / sig : x[k]) : 0.f;
+    if (drop_thr != 0u) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(c >> 2) + j, static_cast<uint32_t>(row), 0u, 0u,
+                                          static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+        x[4 * j + 0] = ((rnd.x >> 8) >= drop_thr) ? x[4 * j + 0] * keep_inv : 0.f;
+        x[4 * j + 1] = ((rnd.y >> 8) >= drop_thr) ? x[4 * j + 1] * keep_inv : 0.f;
+        x[4 * j + 2] = ((rnd.z >> 8) >= drop_thr) ? x[4 * j + 2] * keep_inv : 0.f;
+        x[4 * j + 3] = ((rnd.w >> 8) >= drop_thr) ? x[4 * j + 3] * keep_inv : 0.f;
+      }
+    }
+    store8(y_hi, y_lo, base + c, x);
+  }
+}
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(__nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
+                  const __nv_bfloat16* __restrict__ u_hi, const __nv_bfloat16* __restrict__ u_lo,
+                  const float* __restrict__ s_in, int ld, int B, int N, int act) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const size_t base = static_cast<size_t>(row) * ld;
+  const float sig = s_in[row];
+  const bool norm = sig > 1.0f;
+  float dot = 0.f;
+  if (norm) {
+    for (int c = lane * 8; c < ld; c += 256) {
+      float d[8], u[8];
+      load8(d_hi, d_lo, base + c, d);
+      load8(u_hi, u_lo, base + c, u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dot += (c + k < N) ? d[k] * u[k] : 0.f;
+    }
+    dot = warp_sum(dot);
+  }
+  const float inv = norm ? 1.0f / sig : 1.0f;
+  const float coef = norm ? 2.0f * dot / (static_cast<float>(N) * sig * sig) : 0.f;
+  for (int c = lane * 8; c < ld; c += 256) {
+    float d[8], u[8];
+    load8(d_hi, d_lo, base + c, d);
+    load8(u_hi, u_lo, base + c, u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float g = (c + k < N) ? d[k] * inv - u[k] * coef : 0.f;
+      if (act == 1) g = u[k] > 0.f ? g : 0.f;
+      else if (act == 2) g *= u[k] * (1.0f - u[k]);
+      else if (act == 3) g *= 1.0f - u[k] * u[k];
+      d[k] = g;
+    }
+    store8(d_hi, d_lo, base + c, d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256)
 decode_out_kernel(const float* __restrict__ logits, int ld, int T, int O, const float* __restrict__ prior,
@@ -642,10 +734,10 @@ int k_merge_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld_src, f
   return static_cast<int>(cudaGetLastError());
 }
 
-int k_mask_scale_f32(const float* dy, const float* y, float* out, size_t n, float scale, int nonzero,
+int k_mask_scale_f32(const float* dy, const float* y, float* out, size_t n, float scale, int mode,
                      cudaStream_t st) {
   if (n == 0) return 0;
-  mask_scale_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(dy, y, out, n, scale, nonzero);
+  mask_scale_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(dy, y, out, n, scale, mode);
   return static_cast<int>(cudaGetLastError());
 }
 int k_double_to_float(const double* src, float* dst, cudaStream_t st) {
@@ -761,6 +853,20 @@ int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat
   if (B <= 0) return 0;
   const size_t total = static_cast<size_t>(B) * (ld >> 3);
   bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_l2norm_fwd(const __nv_bfloat16* u_hi, const __nv_bfloat16* u_lo, int ld, int B, int N, float keep,
+                 unsigned long long seed, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* s_out, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
+  l2norm_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(u_hi, u_lo, ld, B, N, thr, 1.0f / keep, seed, y_hi, y_lo, s_out);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_l2norm_bwd(__nv_bfloat16* d_hi, __nv_bfloat16* d_lo, const __nv_bfloat16* u_hi, const __nv_bfloat16* u_lo,
+                 const float* s_in, int ld, int B, int N, int act, cudaStream_t st) {
+  if (B <= 0) return 0;
+  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(d_hi, d_lo, u_hi, u_lo, s_in, ld, B, N, act);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -16,8 +16,9 @@ int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* 
 int k_merge_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld_src, float* dst, int ld_dst,
                  int rows, int cols, cudaStream_t st);
 
-// out[i] = pass(y[i]) ? dy[i] * scale : 0, pass = (y > 0) or (y != 0): activation-chain backward on fp32
-int k_mask_scale_f32(const float* dy, const float* y, float* out, size_t n, float scale, int nonzero,
+// activation-chain backward on fp32: out = dy * f'(.) * dropmask / keep reconstructed from the stored output y
+// mode 0: relu (y > 0), 1: linear+dropout (y != 0), 2: sigmoid, 3: tanh; +4 when dropout is in the chain
+int k_mask_scale_f32(const float* dy, const float* y, float* out, size_t n, float scale, int mode,
                      cudaStream_t st);
 // dst[0] = (float)src[0]
 int k_double_to_float(const double* src, float* dst, cudaStream_t st);
@@ -59,7 +60,7 @@ int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int l
 // mean/rstd from the moving statistics (eval mode)
 int k_bn_eval_stats(const float* moving_mean, const float* moving_var, int N, float eps, float* mean,
                     float* rstd, cudaStream_t st);
-// y = dropout(relu((z - mean) * rstd + beta)); z,y bf16 hi(+lo) [B, ld]
+// y = dropout(act((z - mean) * rstd + beta)), act code `relu`: 0 none, 1 relu, 2 sigmoid, 3 tanh; z,y bf16 hi(+lo) [B, ld]
 int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N,
                const float* mean, const float* rstd, const float* beta, int relu, float keep,
                unsigned long long seed, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st);
@@ -71,6 +72,17 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                    const float* rstd, const float* sums, cudaStream_t st);
+
+// L2Norm (reference: classifiers/activation.py:87-111, quirk kept): s = mean over columns of u^2 (per frame);
+// y = u / s if s > 1 else u  (divides by the mean SQUARE, not its root), then dropout.  u: output of the
+// nonlinearity, bf16 hi(+lo) [B, ld]; y likewise; s_out fp32 [B].
+int k_l2norm_fwd(const __nv_bfloat16* u_hi, const __nv_bfloat16* u_lo, int ld, int B, int N, float keep,
+                 unsigned long long seed, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* s_out, cudaStream_t st);
+// backward, in place over d (= d loss / d y, dropout already undone): for s > 1
+//   du_j = d_j / s - u_j * (2 / (N s^2)) * sum_k d_k u_k ;  else du = d ;  then the nonlinearity's slope taken
+// from u (act 1 relu: u > 0, 2 sigmoid: u(1-u), 3 tanh: 1-u^2, 0 none).
+int k_l2norm_bwd(__nv_bfloat16* d_hi, __nv_bfloat16* d_lo, const __nv_bfloat16* u_hi, const __nv_bfloat16* u_lo,
+                 const float* s_in, int ld, int B, int N, int act, cudaStream_t st);
 
 // Decoder output (reference: neuralNetworks/decoder.py:44 softmax; nnet.py:280-286 log(P/prior)):
 //   prior == null : out = softmax(z)          (Decoder.__call__)

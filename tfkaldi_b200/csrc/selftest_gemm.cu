@@ -144,7 +144,7 @@ static bool run_case(const Case& c, std::mt19937& rng, int nsamples) {
   s.B_hi = B.d_hi; s.B_lo = B.d_lo; s.ldb = ldB; s.b_mn = c.b_mn;
   s.nsplit = c.nsplit; s.out_kind = c.out_kind; s.ksplit = c.ksplit;
   s.D_hi = D_hi; s.D_lo = D_lo; s.ldd = ldd;
-  s.bias = dbias; s.relu = c.relu;
+  s.bias = dbias; s.act = c.relu ? 1 : 0;
   if (c.mask) { s.mask_src = Mk.d_hi; s.mask_ld = ldm; s.scale = 2.0f; }
   if (c.dropout) { s.keep = 0.5f; s.seed = 0x1234567890abcdefULL; }
   if (c.stats) { s.stat_sum = dsum; s.stat_sq = dsq; s.stat_ld = stat_ld; }
@@ -334,7 +334,7 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   GemmSpec s; s.M = M; s.N = N; s.K = K;
   s.A_hi = A.d_hi; s.A_lo = A.d_lo; s.lda = A.ld; s.a_mn = a_mn;
   s.B_hi = B.d_hi; s.B_lo = B.d_lo; s.ldb = B.ld; s.b_mn = b_mn;
-  s.nsplit = nsplit; s.out_kind = out_kind; s.D_hi = D; s.D_lo = Dl; s.ldd = N; s.bias = bias; s.relu = !f32out;
+  s.nsplit = nsplit; s.out_kind = out_kind; s.D_hi = D; s.D_lo = Dl; s.ldd = N; s.bias = bias; s.act = f32out ? 0 : 1;
   GemmParams P; char err[256];
   if (build(&s, 1, &P, err, sizeof(err))) { printf("bench build failed %s\n", err); return; }
   for (int i = 0; i < 3; ++i) gemm_launch(P, g_sms, 0);

@@ -22,7 +22,7 @@ class Engine:
     (neuralNetworks/nnet.py:134, trainer.py:37-215, decoder.py:20-47)."""
 
     def __init__(self, num_layers, input_dim, hidden_dim, output_dim, max_frames, *, nonlin="relu",
-                 batch_norm=False, keep_prob=1.0, precision="bf16", device=None, seed=0):
+                 batch_norm=False, keep_prob=1.0, precision="bf16", device=None, seed=0, l2_norm=False):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise RuntimeError("tfkaldi_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -33,14 +33,16 @@ class Engine:
         self.lib.tfk_default_config(C.byref(cfg))
         cfg.num_layers, cfg.input_dim, cfg.hidden_dim, cfg.output_dim = num_layers, input_dim, hidden_dim, output_dim
         cfg.max_frames = int(max_frames)
-        if nonlin not in ("relu", "linear"):
+        codes = {"relu": L.TFK_NONLIN_RELU, "linear": L.TFK_NONLIN_LINEAR, "sigmoid": L.TFK_NONLIN_SIGMOID, "tanh": L.TFK_NONLIN_TANH}
+        if nonlin not in codes:
             raise Exception("unkown nonlinearity")  # neuralNetworks/nnet.py:65 (sic)
-        cfg.nonlin = L.TFK_NONLIN_RELU if nonlin == "relu" else L.TFK_NONLIN_LINEAR
+        cfg.nonlin = codes[nonlin]
         cfg.batch_norm = 1 if batch_norm else 0
         cfg.keep_prob = float(keep_prob)
         cfg.precision = {"bf16": L.TFK_PREC_BF16, "bf16x3": L.TFK_PREC_BF16X3}[precision]
         cfg.device = self.device.index
         cfg.seed = int(seed)
+        cfg.l2_norm = 1 if l2_norm else 0
         self.cfg = cfg
         self.precision = precision
         self.num_layers, self.input_dim, self.hidden_dim, self.output_dim = num_layers, input_dim, hidden_dim, output_dim

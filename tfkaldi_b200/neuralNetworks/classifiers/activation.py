@@ -90,7 +90,7 @@ def compile_chain(activation):
     """Activation chain -> engine keyword arguments.  The engine fuses exactly the order Nnet builds
     (nnet.py:42-72); anything else is refused loudly instead of being silently re-ordered."""
     stages = activation.stages() if activation is not None else []
-    spec = {"batch_norm": False, "nonlin": "linear", "keep_prob": 1.0}
+    spec = {"batch_norm": False, "nonlin": "linear", "keep_prob": 1.0, "l2_norm": False}
     order = {"batchnorm": 0, "nonlin": 1, "l2norm": 2, "dropout": 3}
     last = -1
     for kind, arg in stages:
@@ -100,11 +100,9 @@ def compile_chain(activation):
         if kind == "batchnorm":
             spec["batch_norm"] = True
         elif kind == "nonlin":
-            if arg not in ("relu", "linear"):
-                raise NotImplementedError("nonlinearity %r: only relu and linear have sm_100a epilogues so far" % arg)
-            spec["nonlin"] = arg
+            spec["nonlin"] = arg  # relu / sigmoid / tanh / linear (nnet.py:47-62)
         elif kind == "l2norm":
-            raise NotImplementedError("L2Norm (activation.py:87-111) has no sm_100a epilogue yet (SURVEY.md 8f rank 3)")
+            spec["l2_norm"] = True
         elif kind == "dropout":
             spec["keep_prob"] = arg
     return spec

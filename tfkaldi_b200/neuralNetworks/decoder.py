@@ -17,7 +17,7 @@ class Decoder(object):
         self.input_dim = input_dim
         self.engine = Engine(spec["num_layers"], spec["input_dim"], spec["hidden_dim"], spec["output_dim"],
                              min(int(max_frames), max(int(max_length), 1)), nonlin=spec["nonlin"],
-                             batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"], precision=precision, device=device)
+                             batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"], l2_norm=spec["l2_norm"], precision=precision, device=device)
         self._trainer_like = None
 
     def __call__(self, inputs):

@@ -131,7 +131,7 @@ class Trainer(object, metaclass=ABCMeta):
             max_frames = int(numutterances_per_minibatch) * int(max_input_length)
         self.max_frames = int(max_frames)
         self.engine = Engine(spec["num_layers"], spec["input_dim"], spec["hidden_dim"], spec["output_dim"], self.max_frames,
-                             nonlin=spec["nonlin"], batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"],
+                             nonlin=spec["nonlin"], batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"], l2_norm=spec["l2_norm"],
                              precision=precision, device=device, seed=seed)
         if distributed:
             self.engine.init_comm_from_torch()
