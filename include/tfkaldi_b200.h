@@ -128,6 +128,20 @@ int tfk_softmax_ce(tfk_handle* h, const float* logits, const int32_t* labels, in
  * x: fp32 [B, input_dim] packed frames (utterance-major, no padding), labels: int32 [B]. */
 int tfk_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, void* stream);
 
+/* Device-side feeder: the same as tfk_accumulate / tfk_forward_loglik, but from RAW
+ * (un-normalised, un-spliced) frames; CMVN and the +-context splice of FeatureReader.get_utt
+ * (processing/feature_reader.py:42-60, 91-156) run on the device, fused with the operand conversion.
+ *   raw          fp32 [R, feat_dim], the utterances packed one after the other
+ *   utt_offsets  int32 [num_utts + 1] first row of every utterance (utt_offsets[num_utts] == R)
+ *   cmvn         fp32 [num_utts, 2, feat_dim]: per utterance the speaker's mean and 1/sqrt(variance)
+ *   labels       int32 [R];   feat_dim * (2*context + 1) must equal input_dim
+ * Rows beyond an utterance's edges are zero, exactly as the reference's splice.  (Utterances shorter than
+ * 2*context+1 frames are dropped by the reference's dispenser; the caller filters them the same way.) */
+int tfk_accumulate_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                       const int32_t* labels, int R, int feat_dim, int context, void* stream);
+int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                           int R, int feat_dim, int context, const float* prior, float* out, void* stream);
+
 /* == `run([average_loss, apply_gradients_op])` + init_grads/init_loss/init_num_frames
  * (trainer.py:174-184, 337-352): [allreduce over ranks] -> grads / num_frames -> clip[-1,1] -> Adam
  * (TF form) -> global_step += 1 -> accumulators re-zeroed.  `lr` is the decayed learning rate

@@ -340,3 +340,48 @@ def test_errors_are_loud(cuda_device):
         eng.get_tensor(L.T_BN_BETA, 0)  # no batch norm configured
     with pytest.raises(Exception):
         Engine(2, 40, 32, 10, 64, nonlin="softsign")
+
+
+def test_device_side_cmvn_splice_feeder_matches_host_pipeline(cuda_device):
+    """tfk_accumulate_raw / tfk_forward_loglik_raw (CMVN + +-k splice on the device)
+    against the host pipeline apply_cmvn -> splice -> tfk_accumulate (processing/feature_reader.py:91-156):
+    same gradients, same loss, same log-likelihoods — including utterance edges and, in the decoder,
+    windows that straddle the max_frames tile border."""
+    from tfkaldi_b200 import _lib as L
+    from tfkaldi_b200.engine import Engine
+    from tfkaldi_b200.processing.feature_reader import apply_cmvn, splice
+
+    rng = np.random.default_rng(21)
+    D, K, O = 40, 5, 183
+    lens = [37, 11, 64, 23]  # 11 == 2k+1: the shortest utterance the reference keeps
+    raw = [(rng.standard_normal((t, D)) * 3 + 1).astype(np.float32) for t in lens]
+    stats = []
+    for x in raw:  # per-utterance statistics in the reference's [2, D+1] layout
+        s = np.zeros((2, D + 1), np.float32)
+        s[0, :-1], s[0, -1], s[1, :-1] = x.sum(0), x.shape[0], np.square(x).sum(0)
+        stats.append(s)
+    spliced = np.concatenate([splice(apply_cmvn(x, s), K) for x, s in zip(raw, stats)])
+    cmvn = np.stack([np.stack([s[0, :-1] / s[0, -1], 1.0 / np.sqrt(s[1, :-1] / s[0, -1] - np.square(s[0, :-1] / s[0, -1]))]) for s in stats]).astype(np.float32)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    labels = rng.integers(0, O, sum(lens))
+    cfg = OracleConfig(num_layers=2, input_dim=D * (2 * K + 1), hidden_dim=256, output_dim=O, nonlin="linear")
+    params = reference_init(cfg, rng)
+    params["W2"] = (rng.standard_normal((256, O)) / 16).astype(np.float32)
+    a = Engine(2, 440, 256, O, 256, nonlin="linear", precision="bf16x3")
+    b = Engine(2, 440, 256, O, 256, nonlin="linear", precision="bf16x3")
+    a.load_params(params)
+    b.load_params(params)
+    a.accumulate(spliced, labels)
+    b.accumulate_raw(np.concatenate(raw), offsets, cmvn, labels, D, K)
+    for l in range(3):
+        ga, gb = a.get_tensor(L.T_GRAD_W, l), b.get_tensor(L.T_GRAD_W, l)
+        assert np.abs(ga - gb).max() <= 2e-5 * np.abs(ga).max(), l  # CMVN divides on the host, multiplies by 1/std here
+    assert abs(a.apply(1e-3) - b.apply(1e-3)) < 1e-5
+    prior = np.full(O, 1.0 / O, np.float32)
+    small = Engine(2, 440, 256, O, 48, nonlin="linear", precision="bf16x3")  # 135 frames over 48-frame tiles
+    small.load_params(params)
+    want = a.loglik(spliced, prior).cpu().numpy()
+    got = small.loglik_raw(np.concatenate(raw), offsets, cmvn, D, K, prior).cpu().numpy()
+    assert close(got, want) < 1e-4
+    with pytest.raises(L.TfkError):
+        b.accumulate_raw(np.concatenate(raw), offsets, cmvn, labels, D, 4)  # 40 * 9 != 440

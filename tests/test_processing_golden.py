@@ -144,3 +144,25 @@ def test_alignment_coder(corpus):
     with pytest.raises(KeyError):
         coder.encode("3 11")  # not in the alphabet
     assert sorted(readfiles.read_utt2spk("utt2spk").items()) == [tuple(map(str, kv)) for kv in GOLD["utt2spk_keys"]]
+
+
+def test_raw_batches_select_the_same_utterances(corpus, capsys):
+    """get_raw_batch (device-side feeder) walks the archive exactly like get_batch: same utterances, same
+    targets, same warnings; cmvn+splice of its raw matrices reproduces get_batch's features bit for bit."""
+    from tfkaldi_b200.processing import batchdispenser, feature_reader, target_coder
+
+    def make():
+        reader = feature_reader.FeatureReader("feats.scp", "cmvn.scp", "utt2spk", 2, 15)
+        return reader, batchdispenser.AlignmentBatchDispenser(reader, target_coder.AlignmentCoder(lambda x, y: x, 11), 2, "pdf.all.gz")
+
+    _, a = make()
+    _, b = make()
+    capsys.readouterr()
+    for _ in range(3):
+        x, y = a.get_batch()
+        out_a = capsys.readouterr().out
+        raw, stats, y2 = b.get_raw_batch()
+        assert capsys.readouterr().out == out_a
+        for xi, ri, si, ya, yb in zip(x, raw, stats, y, y2):
+            assert np.array_equal(feature_reader.splice(feature_reader.apply_cmvn(ri, si), 2), xi)
+            assert np.array_equal(ya, yb)

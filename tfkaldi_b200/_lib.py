@@ -64,6 +64,8 @@ SIGNATURES = [
     ("tfk_fflayer_bwd", C.c_int, [_H, C.c_int, _FP, _FP, C.c_int, C.c_void_p]),
     ("tfk_softmax_ce", C.c_int, [_H, _FP, _FP, C.c_int, _FP, _FP, C.c_void_p]),
     ("tfk_accumulate", C.c_int, [_H, _FP, _FP, C.c_int, C.c_void_p]),
+    ("tfk_accumulate_raw", C.c_int, [_H, _FP, _FP, C.c_int, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("tfk_forward_loglik_raw", C.c_int, [_H, _FP, _FP, C.c_int, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, C.c_void_p]),
     ("tfk_apply", C.c_int, [_H, C.c_float, C.POINTER(C.c_float), C.c_void_p]),
     ("tfk_eval_accumulate", C.c_int, [_H, _FP, _FP, C.c_int, C.c_void_p]),
     ("tfk_eval_finish", C.c_int, [_H, C.POINTER(C.c_float), C.c_void_p]),

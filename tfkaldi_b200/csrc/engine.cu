@@ -849,7 +849,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     CREATE_TRY(dev_alloc(h, &h->bn_ps, n));
     CREATE_TRY(dev_alloc(h, &h->bn_pq, n));
   }
-  CREATE_TRY(dev_alloc(h, &h->ws, 64 * static_cast<size_t>(h->ldmax)));        // bn backward partials
+  CREATE_TRY(dev_alloc(h, &h->ws, 256 * static_cast<size_t>(h->ldmax)));       // bn backward partials [128][2][ld]
   CREATE_TRY(dev_alloc(h, &h->ws_colsum, 1024 + 64 * static_cast<size_t>(h->ldmax)));  // colsum counters + partials
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
@@ -1082,6 +1082,64 @@ int tfk_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, 
   return TFK_OK;
 }
 
+static int check_raw(tfk_handle* h, const char* what, int feat_dim, int context, int num_utts) {
+  if (feat_dim < 1 || context < 0 || num_utts < 1)
+    return fail(h, TFK_EINVAL, "%s: feat_dim=%d context=%d num_utts=%d", what, feat_dim, context, num_utts);
+  if (feat_dim * (2 * context + 1) != h->cfg.input_dim)
+    return fail(h, TFK_ESHAPE, "%s: feat_dim %d x (2*%d+1) != input_dim %d", what, feat_dim, context, h->cfg.input_dim);
+  return TFK_OK;
+}
+
+static int load_raw(tfk_handle* h, const float* raw, const int32_t* utt_off, int num_utts, const float* cmvn,
+                    int feat_dim, int context, int row_begin, int rows, cudaStream_t st) {
+  TimerScope ts(h, st, TFK_TIMER_CONVERT);
+  TFK_LAUNCH(h, k_splice_cmvn(raw, utt_off, num_utts, cmvn, feat_dim, context, row_begin, rows, h->act_hi[0],
+                              h->act_lo[0], h->ld0, st));
+  return TFK_OK;
+}
+
+int tfk_accumulate_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                       const int32_t* labels, int R, int feat_dim, int context, void* stream) {
+  if (!h || !raw || !utt_offsets || !cmvn || !labels) return fail(h, TFK_EINVAL, "tfk_accumulate_raw: null argument");
+  TFK_TRY(check_frames(h, R, "tfk_accumulate_raw"));
+  TFK_TRY(check_raw(h, "tfk_accumulate_raw", feat_dim, context, num_utts));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, R, &plan));
+  TFK_TRY(load_raw(h, raw, utt_offsets, num_utts, cmvn, feat_dim, context, 0, R, st));
+  TFK_TRY(forward_range(h, *plan, R, true, 0, true, st));
+  TFK_TRY(ce_and_backward(h, *plan, labels, R, true, st));
+  h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  return TFK_OK;
+}
+
+int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                           int R, int feat_dim, int context, const float* prior, float* out, void* stream) {
+  if (!h || !raw || !utt_offsets || !cmvn || !out) return fail(h, TFK_EINVAL, "tfk_forward_loglik_raw: null argument");
+  if (R <= 0) return fail(h, TFK_ESHAPE, "tfk_forward_loglik_raw: R=%d must be positive", R);
+  TFK_TRY(check_raw(h, "tfk_forward_loglik_raw", feat_dim, context, num_utts));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int O = h->cfg.output_dim, maxB = h->cfg.max_frames;
+  const float* log_prior = nullptr;
+  if (prior) {
+    TFK_LAUNCH(h, k_log_vector(prior, h->tmp_f32, O, st));
+    h->launches += 1;
+    log_prior = h->tmp_f32;
+  }
+  for (int t0 = 0; t0 < R; t0 += maxB) {  // the splice reads across chunk borders straight from `raw`
+    const int B = (R - t0 < maxB) ? (R - t0) : maxB;
+    Plan* plan;
+    TFK_TRY(get_plan(h, B, &plan));
+    TFK_TRY(load_raw(h, raw, utt_offsets, num_utts, cmvn, feat_dim, context, t0, B, st));
+    TFK_TRY(forward_range(h, *plan, B, false, 0, true, st));
+    TimerScope ts(h, st, TFK_TIMER_DECODE_OUT);
+    TFK_LAUNCH(h, k_decode_out(h->logits, h->ldo, B, O, log_prior, out + static_cast<size_t>(t0) * O, st));
+  }
+  return TFK_OK;
+}
+
 int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (!h) return TFK_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1159,6 +1217,13 @@ static int forward_decode(tfk_handle* h, const float* x, int T, const float* pri
   if (T <= 0) return fail(h, TFK_ESHAPE, "decode: T=%d must be positive", T);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
   const int I = h->cfg.input_dim, O = h->cfg.output_dim, maxB = h->cfg.max_frames;
+  const float* log_prior = nullptr;
+  if (prior) {  // log(prior) once per call, into the (otherwise idle) gradient-side scratch
+    float* lp = h->tmp_f32;
+    TFK_LAUNCH(h, k_log_vector(prior, lp, O, st));
+    h->launches += 1;
+    log_prior = lp;
+  }
   for (int t0 = 0; t0 < T; t0 += maxB) {  // frames are independent: tile long utterances over the workspace
     const int B = (T - t0 < maxB) ? (T - t0) : maxB;
     Plan* plan;
@@ -1166,7 +1231,7 @@ static int forward_decode(tfk_handle* h, const float* x, int T, const float* pri
     TFK_TRY(load_input(h, x + static_cast<size_t>(t0) * I, B, 0, st));
     TFK_TRY(forward_range(h, *plan, B, false, 0, true, st));
     TimerScope ts(h, st, TFK_TIMER_DECODE_OUT);
-    TFK_LAUNCH(h, k_decode_out(h->logits, h->ldo, B, O, prior, out + static_cast<size_t>(t0) * O, st));
+    TFK_LAUNCH(h, k_decode_out(h->logits, h->ldo, B, O, log_prior, out + static_cast<size_t>(t0) * O, st));
   }
   return TFK_OK;
 }

@@ -62,6 +62,39 @@ __global__ void split_f32_kernel(const float* __restrict__ src, int ld_src, __nv
   }
 }
 
+// one warp per output row: find the row's utterance (binary search, warp-uniform), then lanes stride over
+// the (2k+1)*D output columns; neighbouring rows re-read the same raw frames from L1/L2.
+__global__ void __launch_bounds__(256)
+splice_cmvn_kernel(const float* __restrict__ raw, const int32_t* __restrict__ utt_off, int num_utts,
+                   const float* __restrict__ cmvn, int D, int k, int row_begin, int rows,
+                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_dst) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= rows) return;
+  const int r = row_begin + i;
+  int a = 0, b = num_utts;  // utt_off[a] <= r < utt_off[b]
+  while (b - a > 1) {
+    const int m = (a + b) >> 1;
+    if (__ldg(utt_off + m) <= r) a = m; else b = m;
+  }
+  const int u0 = __ldg(utt_off + a), u1 = __ldg(utt_off + a + 1);
+  const float* __restrict__ mean = cmvn + static_cast<size_t>(a) * 2 * D;
+  const float* __restrict__ istd = mean + D;
+  const int width = (2 * k + 1) * D;
+  const size_t o = static_cast<size_t>(i) * ld_dst;
+  for (int c = lane; c < ld_dst; c += 32) {
+    float v = 0.f;
+    if (c < width) {
+      const int j = c / D, d = c - j * D;
+      const int src = r + j - k;
+      if (src >= u0 && src < u1) v = (__ldg(raw + static_cast<size_t>(src) * D + d) - __ldg(mean + d)) * __ldg(istd + d);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o + c] = h;
+    if (lo) lo[o + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 __global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                   int ld_src, float* __restrict__ dst, int ld_dst, int rows, int cols) {
   const size_t total = static_cast<size_t>(rows) * cols;
@@ -139,10 +172,10 @@ softmax_ce_kernel(const float* __restrict__ logits, int ld, const int32_t* __res
       const int t = label & 3;
       zl = t == 0 ? z[i].x : t == 1 ? z[i].y : t == 2 ? z[i].z : z[i].w;
     }
-    z[i].x = expf(z[i].x - mx);
-    z[i].y = expf(z[i].y - mx);
-    z[i].z = expf(z[i].z - mx);
-    z[i].w = expf(z[i].w - mx);
+    z[i].x = __expf(z[i].x - mx);
+    z[i].y = __expf(z[i].y - mx);
+    z[i].z = __expf(z[i].z - mx);
+    z[i].w = __expf(z[i].w - mx);
     sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
     (void)e;
   }
@@ -215,7 +248,7 @@ __global__ void __launch_bounds__(1024) accum_loss_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int COLSUM_RS = 32;   // row splits of the BN-backward reductions
+constexpr int COLSUM_RS = 128;  // row splits of the BN-backward reductions
 constexpr int COLSUM2_RS = 64;  // row splits of colsum_kernel
 // Single launch, deterministic.  A warp reads 256 consecutive columns (16 B per lane) of one row per
 // load; a block's 8 warps stride over its row range; the LAST block to finish a 256-column group adds
@@ -263,9 +296,12 @@ colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restr
   __threadfence();
   const int c = blockIdx.x * 256 + t;
   if (c < cols) {
+    float part[COLSUM2_RS];
+#pragma unroll
+    for (int r = 0; r < COLSUM2_RS; ++r) part[r] = __ldcg(ws + static_cast<size_t>(r) * ld + c);  // all in flight
     float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < COLSUM2_RS; ++r) s += __ldcg(ws + static_cast<size_t>(r) * ld + c);
+#pragma unroll
+    for (int r = 0; r < COLSUM2_RS; ++r) s += part[r];  // fixed order
     out[c] += s;
   }
   if (t == 0) counters[blockIdx.x] = 0u;
@@ -279,22 +315,30 @@ struct ColsumJobs {
   int groups, ld, cols, njobs;
 };
 __global__ void __launch_bounds__(256) colsum_finalize_kernel(const ColsumJobs J) {
-  __shared__ float sm[4][64];
+  __shared__ float sm[8][32];
   const float* __restrict__ part = J.part[blockIdx.y];
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int g0 = threadIdx.x >> 6;  // 4 group lanes
-  float s0 = 0.f, s1 = 0.f;
+  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;  // 32 columns x 8 group lanes
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
   if (c < J.cols) {
-    int g = g0;
-    for (; g + 4 < J.groups; g += 8) {
-      s0 += part[static_cast<size_t>(g) * J.ld + c];
-      s1 += part[static_cast<size_t>(g + 4) * J.ld + c];
+    int g = gl;
+    for (; g + 56 < J.groups; g += 64) {  // 8 independent loads in flight
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = part[static_cast<size_t>(g + 8 * k) * J.ld + c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += t[k];
     }
-    for (; g < J.groups; g += 4) s0 += part[static_cast<size_t>(g) * J.ld + c];
+    for (; g < J.groups; g += 8) s += part[static_cast<size_t>(g) * J.ld + c];
   }
-  sm[g0][threadIdx.x & 63] = s0 + s1;
+  sm[gl][cl] = s;
   __syncthreads();
-  if (g0 == 0 && c < J.cols) J.out[blockIdx.y][c] += (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
+  if (gl == 0 && c < J.cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += sm[k][cl];
+    J.out[blockIdx.y][c] += tot;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -342,17 +386,31 @@ adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// block = 32 columns x 8 group lanes; fixed summation order (lane-strided, then lanes 0..7) in double
-__global__ void __launch_bounds__(256)
+// block = 32 columns x 32 group lanes; fixed summation order (lane-strided, then lanes 0..31) in double
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups, int ld, int N,
                    int rows, float eps, float decay, float* __restrict__ mean, float* __restrict__ rstd,
                    float* __restrict__ mm, float* __restrict__ mv) {
-  __shared__ double sm[2][8][32];
+  __shared__ double sm[2][32][33];
   const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
   if (c < N) {
-    for (int gidx = gl; gidx < groups; gidx += 8) {
+    int gidx = gl;
+    for (; gidx + 96 < groups; gidx += 128) {  // 8 loads in flight
+      float a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] = ps[static_cast<size_t>(gidx + 32 * k) * ld + c];
+        b[k] = pq[static_cast<size_t>(gidx + 32 * k) * ld + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s1 += static_cast<double>(a[k]);
+        s2 += static_cast<double>(b[k]);
+      }
+    }
+    for (; gidx < groups; gidx += 32) {
       s1 += static_cast<double>(ps[static_cast<size_t>(gidx) * ld + c]);
       s2 += static_cast<double>(pq[static_cast<size_t>(gidx) * ld + c]);
     }
@@ -363,8 +421,8 @@ bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, i
   if (gl != 0 || c >= N) return;
   s1 = 0.0;
   s2 = 0.0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
     s1 += sm[0][k][cl];
     s2 += sm[1][k][cl];
   }
@@ -415,31 +473,33 @@ __device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, siz
   if (lo) *reinterpret_cast<uint4*>(lo + o) = l;
 }
 
+// thread = one 8-column group (its mean / rstd / beta live in registers); blockIdx.y strides over the rows
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
                 int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ beta, int relu, unsigned int drop_thr, float keep_inv,
                 unsigned long long seed, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
-  const int groups = ld >> 3;
-  const size_t total = static_cast<size_t>(B) * groups;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / groups);
-    const int c = static_cast<int>(i - static_cast<size_t>(r) * groups) << 3;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
+  if (c >= ld) return;
+  float mu[8], rs[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool ok = c + k < N;
+    mu[k] = ok ? mean[c + k] : 0.f;
+    rs[k] = ok ? rstd[c + k] : 0.f;
+    be[k] = ok ? beta[c + k] : 0.f;
+  }
+  for (int r = blockIdx.y; r < B; r += gridDim.y) {
     const size_t o = static_cast<size_t>(r) * ld + c;
     float x[8];
     load8(z_hi, z_lo, o, x);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int col = c + k;
-      float y = 0.f;
-      if (col < N) {
-        y = (x[k] - mean[col]) * rstd[col] + beta[col];
-        if (relu == 1) y = fmaxf(y, 0.f);
-        else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
-        else if (relu == 3) y = tanhf(y);
-      }
-      x[k] = y;
+      float y = (x[k] - mu[k]) * rs[k] + be[k];
+      if (relu == 1) y = fmaxf(y, 0.f);
+      else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
+      else if (relu == 3) y = tanhf(y);
+      x[k] = (c + k < N) ? y : 0.f;
     }
     if (drop_thr != 0u) {
 #pragma unroll
@@ -522,27 +582,27 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict
                     const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
                     int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ sums) {
-  const int groups = ld >> 3;
-  const size_t total = static_cast<size_t>(B) * groups;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
+  if (c >= ld) return;
   const float invB = 1.0f / static_cast<float>(B);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / groups);
-    const int c = static_cast<int>(i - static_cast<size_t>(r) * groups) << 3;
+  float mu[8], rs[8], m1[8], m2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool ok = c + k < N;
+    mu[k] = ok ? mean[c + k] : 0.f;
+    rs[k] = ok ? rstd[c + k] : 0.f;
+    m1[k] = ok ? sums[c + k] * invB : 0.f;
+    m2[k] = ok ? sums[ld + c + k] * invB : 0.f;
+  }
+  for (int r = blockIdx.y; r < B; r += gridDim.y) {
     const size_t o = static_cast<size_t>(r) * ld + c;
     float d[8], z[8];
     load8(dy_hi, dy_lo, o, d);
     load8(z_hi, z_lo, o, z);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int col = c + k;
-      float dz = 0.f;
-      if (col < N) {
-        const float rsd = rstd[col];
-        const float xh = (z[k] - mean[col]) * rsd;
-        dz = rsd * (d[k] - sums[col] * invB - xh * (sums[ld + col] * invB));
-      }
-      d[k] = dz;
+      const float xh = (z[k] - mu[k]) * rs[k];
+      d[k] = (c + k < N) ? rs[k] * (d[k] - m1[k] - xh * m2[k]) : 0.f;
     }
     store8(dy_hi, dy_lo, o, d);
   }
@@ -658,14 +718,15 @@ decode_out_kernel(const float* __restrict__ logits, int ld, int T, int O, const 
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    z[i].x = expf(z[i].x - mx);
-    z[i].y = expf(z[i].y - mx);
-    z[i].z = expf(z[i].z - mx);
-    z[i].w = expf(z[i].w - mx);
+    z[i].x = __expf(z[i].x - mx);
+    z[i].y = __expf(z[i].y - mx);
+    z[i].z = __expf(z[i].z - mx);
+    z[i].w = __expf(z[i].w - mx);
     sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
   }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
+  const float lsum = logf(sum);
   float* op = out + static_cast<size_t>(row) * O;
   const bool vec_store = (O & 3) == 0;
 #pragma unroll
@@ -674,9 +735,15 @@ decode_out_kernel(const float* __restrict__ logits, int ld, int T, int O, const 
     if (e >= O) continue;
     float p[4] = {z[i].x * inv, z[i].y * inv, z[i].z * inv, z[i].w * inv};
     if (prior) {
+      // np.log(output/prior) (nnet.py:280-286) evaluated as log(e^(z-max)) - log(sum) - log(prior): one log per
+      // element less; `prior` here is log(prior) (k_decode_out precomputes it); an underflowed posterior keeps
+      // the reference's -inf
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (e + k < O) p[k] = logf(p[k] / __ldg(prior + e + k));  // np.log(output/prior)  nnet.py:280-286
+        if (e + k < O) {
+          const float ez = k == 0 ? z[i].x : k == 1 ? z[i].y : k == 2 ? z[i].z : z[i].w;
+          p[k] = (p[k] > 0.f) ? __logf(ez) - lsum - __ldg(prior + e + k) : -INFINITY - __ldg(prior + e + k);
+        }
     }
     if (vec_store) {
       *reinterpret_cast<float4*>(op + e) = make_float4(p[0], p[1], p[2], p[3]);
@@ -702,8 +769,9 @@ decode_out_generic_kernel(const float* __restrict__ logits, int ld, int T, int O
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
   for (int e = lane; e < O; e += 32) {
-    float p = expf(zp[e] - mx) * inv;
-    if (prior) p = logf(p / prior[e]);
+    const float ez = expf(zp[e] - mx);
+    float p = ez * inv;
+    if (prior) p = (p > 0.f) ? logf(ez) - logf(sum) - prior[e] : -INFINITY - prior[e];  // prior = log(prior)
     out[static_cast<size_t>(row) * O + e] = p;
   }
 }
@@ -723,6 +791,13 @@ int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* 
   const int vec_ok = (ld_src % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   const size_t total = static_cast<size_t>(rows) * (ld_dst >> 2);
   split_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, ld_src, hi, lo, ld_dst, rows, cols, vec_ok);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_splice_cmvn(const float* raw, const int32_t* utt_off, int num_utts, const float* cmvn, int D, int k,
+                  int row_begin, int rows, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  splice_cmvn_kernel<<<(rows + 7) / 8, 256, 0, st>>>(raw, utt_off, num_utts, cmvn, D, k, row_begin, rows, hi, lo, ld_dst);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -787,7 +862,7 @@ int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, 
       J.out[j] = outs[j0 + j];
     }
     J.groups = groups; J.ld = ld; J.cols = cols;
-    dim3 grid((cols + 63) / 64, J.njobs);
+    dim3 grid((cols + 31) / 32, J.njobs);
     colsum_finalize_kernel<<<grid, 256, 0, st>>>(J);
   }
   return static_cast<int>(cudaGetLastError());
@@ -820,7 +895,7 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
 int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int ld, int N, int rows, float eps,
                   float decay, float* mean, float* rstd, float* moving_mean, float* moving_var,
                   cudaStream_t st) {
-  bn_finalize_kernel<<<(N + 31) / 32, 256, 0, st>>>(part_sum, part_sq, groups, ld, N, rows, eps, decay, mean,
+  bn_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(part_sum, part_sq, groups, ld, N, rows, eps, decay, mean,
                                                      rstd, moving_mean, moving_var);
   return static_cast<int>(cudaGetLastError());
 }
@@ -834,9 +909,11 @@ int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int
                __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st) {
   if (B <= 0) return 0;
   const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
-  const size_t total = static_cast<size_t>(B) * (ld >> 3);
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr,
-                                                        1.0f / keep, seed, y_hi, y_lo);
+  const int gx = ((ld >> 3) + 255) / 256;
+  int gy = 148 * 8 / gx;
+  gy = gy > B ? B : gy;
+  bn_apply_kernel<<<dim3(gx, gy), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr, 1.0f / keep,
+                                                 seed, y_hi, y_lo);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
@@ -851,8 +928,10 @@ int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat
                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
                    const float* sums, cudaStream_t st) {
   if (B <= 0) return 0;
-  const size_t total = static_cast<size_t>(B) * (ld >> 3);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
+  const int gx = ((ld >> 3) + 255) / 256;
+  int gy = 148 * 8 / gx;
+  gy = gy > B ? B : gy;
+  bn_bwd_apply_kernel<<<dim3(gx, gy), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -867,6 +946,15 @@ int k_l2norm_bwd(__nv_bfloat16* d_hi, __nv_bfloat16* d_lo, const __nv_bfloat16* 
                  const float* s_in, int ld, int B, int N, int act, cudaStream_t st) {
   if (B <= 0) return 0;
   l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(d_hi, d_lo, u_hi, u_lo, s_in, ld, B, N, act);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void log_vector_kernel(const float* __restrict__ x, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = logf(x[i]);  // log(0) = -inf  ->  +inf log-likelihood, as the reference
+}
+int k_log_vector(const float* x, float* y, int n, cudaStream_t st) {
+  log_vector_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, y, n);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -12,6 +12,15 @@ namespace tfk {
 int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst,
                 int rows, int cols, cudaStream_t st);
 
+// Device-side feeder (reference: processing/feature_reader.py:91-156 apply_cmvn + splice, done on the host
+// there): raw fp32 frames [R, D] of `num_utts` packed utterances (row offsets utt_off[num_utts+1]) ->
+// CMVN with the utterance's (mean, 1/std) from cmvn[num_utts, 2, D] -> +-k spliced rows
+// [x[t-k] .. x[t] .. x[t+k]] with ZEROS beyond the utterance edges -> bf16 hi(+lo) [rows, ld_dst] for rows
+// [row_begin, row_begin + rows).  Writes layer 0's GEMM operand directly: the spliced fp32 matrix (11x the
+// raw bytes for k = 5) never exists.
+int k_splice_cmvn(const float* raw, const int32_t* utt_off, int num_utts, const float* cmvn, int D, int k,
+                  int row_begin, int rows, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst, cudaStream_t st);
+
 // bf16 hi (+lo) [rows, ld_src] -> fp32 [rows, cols] (pitch ld_dst): dst = hi + lo
 int k_merge_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld_src, float* dst, int ld_dst,
                  int rows, int cols, cudaStream_t st);
@@ -64,7 +73,7 @@ int k_bn_eval_stats(const float* moving_mean, const float* moving_var, int N, fl
 int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N,
                const float* mean, const float* rstd, const float* beta, int relu, float keep,
                unsigned long long seed, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st);
-// backward: sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat; g_beta += sum_B dy.  ws >= 64*ld floats
+// backward: sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat; g_beta += sum_B dy.  ws >= 256*ld floats
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                     const float* rstd, float* ws, float* sums, float* g_beta, cudaStream_t st);
@@ -86,8 +95,10 @@ int k_l2norm_bwd(__nv_bfloat16* d_hi, __nv_bfloat16* d_lo, const __nv_bfloat16* 
 
 // Decoder output (reference: neuralNetworks/decoder.py:44 softmax; nnet.py:280-286 log(P/prior)):
 //   prior == null : out = softmax(z)          (Decoder.__call__)
-//   prior != null : out = log(softmax(z)/prior)   (Nnet.decode pseudo log-likelihood, no flooring)
+//   prior != null : out = log(softmax(z)/prior)   (Nnet.decode pseudo log-likelihood, no flooring);
+//                   `prior` must hold LOG(prior) (k_log_vector), so the kernel needs no per-element log/div
 // out is dense [T, O] fp32.
+int k_log_vector(const float* x, float* y, int n, cudaStream_t st);
 int k_decode_out(const float* logits, int ld, int T, int O, const float* prior, float* out,
                  cudaStream_t st);
 

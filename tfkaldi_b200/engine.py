@@ -138,6 +138,22 @@ class Engine:
         x, labels = self._dev_f32(x), self._dev_i32(labels)
         self._check(self.lib.tfk_accumulate(self.h, _ptr(x), _ptr(labels), x.shape[0], self._stream()))
 
+    def accumulate_raw(self, raw, utt_offsets, cmvn, labels, feat_dim, context):
+        """device-side CMVN + splice feeder: raw [R, D] fp32, utt_offsets int32 [U+1], cmvn [U, 2, D] (mean, 1/std)"""
+        raw, cmvn = self._dev_f32(raw), self._dev_f32(cmvn)
+        utt_offsets, labels = self._dev_i32(utt_offsets), self._dev_i32(labels)
+        self._check(self.lib.tfk_accumulate_raw(self.h, _ptr(raw), _ptr(utt_offsets), utt_offsets.shape[0] - 1, _ptr(cmvn),
+                                                _ptr(labels), raw.shape[0], int(feat_dim), int(context), self._stream()))
+
+    def loglik_raw(self, raw, utt_offsets, cmvn, feat_dim, context, prior, out=None):
+        raw, cmvn, prior = self._dev_f32(raw), self._dev_f32(cmvn), self._dev_f32(prior)
+        utt_offsets = self._dev_i32(utt_offsets)
+        if out is None:
+            out = torch.empty((raw.shape[0], self.output_dim), dtype=torch.float32, device=self.device)
+        self._check(self.lib.tfk_forward_loglik_raw(self.h, _ptr(raw), _ptr(utt_offsets), utt_offsets.shape[0] - 1, _ptr(cmvn),
+                                                    raw.shape[0], int(feat_dim), int(context), _ptr(prior), _ptr(out), self._stream()))
+        return out
+
     def apply(self, lr, want_loss=True):
         if want_loss:
             out = C.c_float()

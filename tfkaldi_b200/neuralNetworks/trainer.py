@@ -256,6 +256,31 @@ class Trainer(object, metaclass=ABCMeta):
             self.prefetch(*prefetch)  # next batch's H2D overlaps this step's kernels
         return self._apply(want_loss)
 
+    def update_raw(self, raw_utts, cmvn_stats, targets, context_width):
+        """update() from RAW features: list of un-normalised [T_u, D] matrices, their speakers' CMVN
+        statistics ([2, D+1], processing/prepare_data.py:114-117) and target vectors.  CMVN and the
+        +-context_width splice (FeatureReader.get_utt, feature_reader.py:42-60) run on the device, so
+        the host uploads D instead of D*(2k+1) values per frame.  Utterances shorter than 2k+1 frames
+        must already be filtered out, as the reference's dispenser does."""
+        n = self.numutterances_per_minibatch
+        if len(raw_utts) % n != 0:
+            raise ValueError("the number of utterances (%d) must be a multiple of numutterances_per_minibatch (%d)" % (len(raw_utts), n))
+        for k in range(len(raw_utts) // n):
+            sl = slice(k * n, (k + 1) * n)
+            mats, stats, tgts = raw_utts[sl], cmvn_stats[sl], targets[sl]
+            lens = [m.shape[0] for m in mats]
+            if min(lens) < 2 * context_width + 1:
+                raise ValueError("utterance too short to splice")
+            offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            cmvn = np.empty((len(mats), 2, mats[0].shape[1]), np.float32)
+            for i, st in enumerate(stats):  # apply_cmvn's formulas (feature_reader.py:109-115)
+                mean = st[0, :-1] / st[0, -1]
+                cmvn[i, 0] = mean
+                cmvn[i, 1] = 1.0 / np.sqrt(st[1, :-1] / st[0, -1] - np.square(mean))
+            labels = np.concatenate(tgts).astype(np.int32)
+            self.engine.accumulate_raw(np.concatenate(mats, axis=0), offsets, cmvn, labels, mats[0].shape[1], context_width)
+        return self._apply()
+
     def _apply(self, want_loss=True):
         step = self.global_step if self.summarywriter is not None else None
         loss = self.engine.apply(self.learning_rate_cached(), want_loss)

@@ -37,6 +37,28 @@ class BatchDispenser(object, metaclass=ABCMeta):
                 print("WARNING %s is too short to splice" % utt_id)
         return batch_inputs, batch_targets
 
+    def get_raw_batch(self):
+        """like get_batch, for the device-side feeder (Trainer.update_raw): returns
+        (raw [T_u, D] matrices, their speakers' CMVN statistics, encoded targets); CMVN and splicing are
+        left to the GPU.  Same utterance selection and warnings as get_batch."""
+        reader = self.feature_reader
+        width = 1 + 2 * reader.context_width
+        mats, stats, batch_targets = [], [], []
+        while len(mats) < self.size:
+            utt_id, utt_mat, _ = reader.reader.read_next_utt()
+            has_targets = utt_id in self.target_dict
+            long_enough = utt_mat.shape[0] >= width
+            if has_targets and long_enough:
+                mats.append(utt_mat)
+                stats.append(reader._cmvn_stats(reader.utt2spk[utt_id]))
+                batch_targets.append(self.target_coder.encode(self.target_dict[utt_id]))
+                continue
+            if not has_targets:
+                print("WARNING no targets for %s" % utt_id)
+            if not long_enough:
+                print("WARNING %s is too short to splice" % utt_id)
+        return mats, stats, batch_targets
+
     def split(self):
         """split off what was read so far (validation set)"""
         self.feature_reader.split()
