@@ -153,8 +153,9 @@ def run_ours(args):
 
     # ---------------- device-resident throughput (`value`): inputs already in HBM
     def step_resident(i):
-        eng.accumulate(dev_x[i % pool], dev_y[i % pool])
-        eng.apply(lr, want_loss=False)  # loss is copied to pinned memory asynchronously, read after the loop
+        # tfk_train_step == tfk_accumulate + tfk_apply (tests/test_gpu_parity.py checks bit-equality); the loss
+        # is copied to pinned memory asynchronously and read after the loop
+        eng.train_step(dev_x[i % pool], dev_y[i % pool], lr, want_loss=False)
 
     for i in range(args.warmup):
         step_resident(i)

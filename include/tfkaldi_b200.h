@@ -150,6 +150,14 @@ int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_o
  * evaluated with the pre-update weights. */
 int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream);
 
+/* == tfk_accumulate + tfk_apply for ONE micro-batch (the reference's update() with
+ * numutterances_per_minibatch covering the whole batch, trainer.py:310-352), same arithmetic; on a single
+ * GPU each layer's clip+Adam update runs on a side stream right after that layer's backward kernel so it
+ * overlaps the remaining backward pass.  Falls back to the plain sequence under data parallelism or when
+ * gradients are already being accumulated. */
+int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, float lr, float* mean_loss_host,
+                   void* stream);
+
 /* == `update_valid_loss.run(feed_dict)` (trainer.py:186-195, 428): eval-mode forward (moving-stat BN,
  * no dropout) + CE; batch_loss += loss, num_frames += B. */
 int tfk_eval_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, void* stream);

@@ -380,8 +380,40 @@ def test_device_side_cmvn_splice_feeder_matches_host_pipeline(cuda_device):
     prior = np.full(O, 1.0 / O, np.float32)
     small = Engine(2, 440, 256, O, 48, nonlin="linear", precision="bf16x3")  # 135 frames over 48-frame tiles
     small.load_params(params)
+    a.load_params(params)  # a's weights moved in apply(); compare on the same parameters
     want = a.loglik(spliced, prior).cpu().numpy()
     got = small.loglik_raw(np.concatenate(raw), offsets, cmvn, D, K, prior).cpu().numpy()
     assert close(got, want) < 1e-4
     with pytest.raises(L.TfkError):
         b.accumulate_raw(np.concatenate(raw), offsets, cmvn, labels, D, 4)  # 40 * 9 != 440
+
+
+@pytest.mark.parametrize("variant", ["plain", "bn_dropout"])
+def test_fused_train_step_equals_accumulate_plus_apply(cuda_device, variant):
+    """tfk_train_step (per-layer Adam overlapped with the backward pass) is the same arithmetic as
+    tfk_accumulate + tfk_apply: identical losses and bit-identical parameters / Adam slots after 4 steps;
+    with gradients already accumulating it must fall back to the plain sequence."""
+    from tfkaldi_b200 import _lib as L
+
+    cfg = OracleConfig(**{**C1, **VARIANTS[variant]})
+    _, a, rng = make_pair(cfg, 256, "bf16", seed=8, random_out=True)
+    _, b, _ = make_pair(cfg, 256, "bf16", seed=8, random_out=True)
+    for step in range(4):
+        x = rng.standard_normal((256, 440)).astype(np.float32)
+        y = rng.integers(0, 183, 256)
+        a.set_dropout_seed(100 + step)
+        b.set_dropout_seed(100 + step)
+        a.accumulate(x, y)
+        la = a.apply(2e-3)
+        lb = b.train_step(x, y, 2e-3)
+        assert la == lb
+    pa, pb = a.dump_params(), b.dump_params()
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), k
+    for l in range(3):
+        assert np.array_equal(a.get_tensor(L.T_ADAM_V_W, l), b.get_tensor(L.T_ADAM_V_W, l))
+    x2 = rng.standard_normal((128, 440)).astype(np.float32)
+    y2 = rng.integers(0, 183, 128)
+    a.accumulate(x2, y2); a.accumulate(x, y); la = a.apply(1e-3)
+    b.accumulate(x2, y2); lb = b.train_step(x, y, 1e-3)  # open accumulation -> sequential path, two micro-batches
+    assert la == lb and np.array_equal(a.dump_params()["W1"], b.dump_params()["W1"])

@@ -139,6 +139,9 @@ struct tfk_handle {
   bool own_comm = false;
   int rank = 0, nranks = 1;
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t adam_stream = nullptr;      // tfk_train_step: per-layer Adam overlapped with the rest of the backward pass
+  std::vector<cudaEvent_t> layer_events;
+  int pending_accumulates = 0;             // tfk_accumulate calls since the last tfk_apply
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   // timers
   bool timers_on = false;
@@ -703,6 +706,8 @@ int tfk_destroy(tfk_handle* h) {
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->adam_stream) cudaStreamDestroy(h->adam_stream);
+  for (auto e : h->layer_events) cudaEventDestroy(e);
   for (auto& kv : h->plans) free_plan(kv.second);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->allocs) cudaFree(p);
@@ -1079,6 +1084,7 @@ int tfk_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, 
   TFK_TRY(forward_range(h, *plan, B, true, 0, true, st));
   TFK_TRY(ce_and_backward(h, *plan, labels, B, true, st));
   h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  h->pending_accumulates += 1;
   return TFK_OK;
 }
 
@@ -1111,6 +1117,7 @@ int tfk_accumulate_raw(tfk_handle* h, const float* raw, const int32_t* utt_offse
   TFK_TRY(forward_range(h, *plan, R, true, 0, true, st));
   TFK_TRY(ce_and_backward(h, *plan, labels, R, true, st));
   h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  h->pending_accumulates += 1;
   return TFK_OK;
 }
 
@@ -1144,6 +1151,7 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (!h) return TFK_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->pending_accumulates = 0;
   if (h->sharded) TFK_TRY(reduce_scatter_grads(h, st));
   else TFK_TRY(allreduce_grads(h, st));
   h->global_step += 1;  // apply_gradients(global_step=...)   trainer.py:182-184
@@ -1185,6 +1193,92 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (mean_loss_host) {
     TFK_CUDA(h, cudaStreamSynchronize(st));
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);  // average_loss   trainer.py:198
+  }
+  return TFK_OK;
+}
+
+// One whole optimizer step for the common case of ONE micro-batch on ONE GPU
+// (== tfk_accumulate + tfk_apply, same arithmetic): the clip+Adam update of a layer's weights is launched
+// on a side stream as soon as that layer's fused wgrad/dgrad kernel has finished, so the HBM-bound Adam
+// pass overlaps the tensor-bound backward kernels of the layers below instead of following them.
+int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, float lr, float* mean_loss_host,
+                   void* stream) {
+  if (!h || !x || !labels) return fail(h, TFK_EINVAL, "tfk_train_step: null argument");
+  if (h->comm != nullptr || h->pending_accumulates > 0) {  // data parallel / open accumulation: plain sequence
+    TFK_TRY(tfk_accumulate(h, x, labels, B, stream));
+    return tfk_apply(h, lr, mean_loss_host, stream);
+  }
+  TFK_TRY(check_frames(h, B, "tfk_train_step"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (!h->adam_stream) {
+    TFK_CUDA(h, cudaStreamCreateWithFlags(&h->adam_stream, cudaStreamNonBlocking));
+    h->layer_events.resize(h->L + 2);
+    for (auto& e : h->layer_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  Plan* plan;
+  TFK_TRY(get_plan(h, B, &plan));
+  TFK_TRY(load_input(h, x, B, 0, st));
+  TFK_TRY(forward_range(h, *plan, B, true, 0, true, st));
+  {
+    TimerScope ts(h, st, TFK_TIMER_SOFTMAX_CE, 2);
+    TFK_LAUNCH(h, k_softmax_ce(h->logits, h->ldo, labels, B, h->cfg.output_dim, h->row_loss, h->dzo_hi,
+                               h->x3 ? h->dzo_lo : nullptr, st));
+    TFK_LAUNCH(h, k_accum_loss(h->row_loss, B, h->acc, st));  // acc = {loss_sum, frames}: Adam reads frames
+  }
+  h->global_step += 1;
+  const double t = static_cast<double>(h->global_step);
+  const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+  const float lr_t = static_cast<float>(static_cast<double>(lr) * h->lr_fact * std::sqrt(1.0 - std::pow(b2, t)) /
+                                        (1.0 - std::pow(b1, t)));
+  auto adam_layer = [&](int l) -> int {  // weights of layer l, after its backward kernel, on the side stream
+    TFK_CUDA(h, cudaEventRecord(h->layer_events[l], st));
+    TFK_CUDA(h, cudaStreamWaitEvent(h->adam_stream, h->layer_events[l], 0));
+    TimerScope ts(h, h->adam_stream, TFK_TIMER_ADAM);
+    const size_t off = h->layers[l].off_w, cnt = h->layers[l].w_count;
+    TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, &off, &cnt, 1, h->acc, lr_t,
+                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->adam_stream));
+    return TFK_OK;
+  };
+  TFK_TRY(backward_layer(h, *plan, B, h->L, st, nullptr, true));
+  TFK_TRY(adam_layer(h->L));
+  for (int l = h->active - 1; l >= 0; --l) {
+    TFK_TRY(backward_layer(h, *plan, B, l, st, nullptr, true));
+    TFK_TRY(adam_layer(l));
+  }
+  {
+    const float* parts[64];
+    float* outs[64];
+    int n = 0;
+    for (int l = 0; l < h->active; ++l)
+      if (!h->layers[l].bn && !h->cfg.l2_norm) {
+        parts[n] = h->layers[l].db_part;
+        outs[n] = h->G + h->layers[l].off_b;
+        ++n;
+      }
+    if (n > 0) {
+      TimerScope ts(h, st, TFK_TIMER_COLSUM);
+      TFK_LAUNCH(h, k_colsum_finalize(parts, outs, n, (B + 31) / 32, h->ldh, h->cfg.hidden_dim, st));
+    }
+  }
+  {  // biases / betas (small), then inactive layers' weight regions (zero gradients: a no-op update, kept for
+     // exact equivalence with tfk_apply, which always covers the whole arena)
+    TimerScope ts(h, st, TFK_TIMER_ADAM);
+    size_t off[70], cnt[70];
+    int n = 0;
+    off[n] = h->nW; cnt[n] = h->arena_n - h->nW; ++n;
+    for (int l = h->active; l < h->L; ++l) { off[n] = h->layers[l].off_w; cnt[n] = h->layers[l].w_count; ++n; }
+    TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, off, cnt, n, h->acc, lr_t,
+                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
+  }
+  TFK_CUDA(h, cudaEventRecord(h->layer_events[h->L + 1], h->adam_stream));
+  TFK_CUDA(h, cudaStreamWaitEvent(st, h->layer_events[h->L + 1], 0));
+  h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));
+  if (mean_loss_host) {
+    TFK_CUDA(h, cudaStreamSynchronize(st));
+    *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
   }
   return TFK_OK;
 }

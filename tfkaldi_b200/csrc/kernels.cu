@@ -489,10 +489,18 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
     rs[k] = ok ? rstd[c + k] : 0.f;
     be[k] = ok ? beta[c + k] : 0.f;
   }
-  for (int r = blockIdx.y; r < B; r += gridDim.y) {
+  const int step = static_cast<int>(gridDim.y);
+  for (int r0 = blockIdx.y; r0 < B; r0 += 4 * step) {
+    float xs[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)  // four rows' loads in flight before any arithmetic
+      if (r0 + u * step < B) load8(z_hi, z_lo, static_cast<size_t>(r0 + u * step) * ld + c, xs[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    const int r = r0 + u * step;
+    if (r >= B) break;
     const size_t o = static_cast<size_t>(r) * ld + c;
-    float x[8];
-    load8(z_hi, z_lo, o, x);
+    float (&x)[8] = xs[u];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float y = (x[k] - mu[k]) * rs[k] + be[k];
@@ -513,6 +521,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
       }
     }
     store8(y_hi, y_lo, o, x);
+    }
   }
 }
 
@@ -564,14 +573,40 @@ bn_bwd_stage1_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat1
     __syncthreads();
   }
 }
-__global__ void bn_bwd_stage2_kernel(const float* __restrict__ ws, int ld, int N, float* __restrict__ sums,
-                                     float* __restrict__ g_beta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+// block = 32 columns x 8 partial lanes, loads batched; fixed summation order
+__global__ void __launch_bounds__(256)
+bn_bwd_stage2_kernel(const float* __restrict__ ws, int ld, int N, float* __restrict__ sums,
+                     float* __restrict__ g_beta) {
+  __shared__ float sm[2][8][32];
+  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s1 = 0.f, s2 = 0.f;
-  for (int r = 0; r < COLSUM_RS; ++r) {
-    s1 += ws[(static_cast<size_t>(r) * 2 + 0) * ld + c];
-    s2 += ws[(static_cast<size_t>(r) * 2 + 1) * ld + c];
+  if (c < N) {
+    for (int r = gl; r < COLSUM_RS; r += 32) {  // 4 partial rows x 2 arrays in flight
+      float a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = r + 8 * k;
+        a[k] = rr < COLSUM_RS ? ws[(static_cast<size_t>(rr) * 2 + 0) * ld + c] : 0.f;
+        b[k] = rr < COLSUM_RS ? ws[(static_cast<size_t>(rr) * 2 + 1) * ld + c] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s1 += a[k];
+        s2 += b[k];
+      }
+    }
+  }
+  sm[0][gl][cl] = s1;
+  sm[1][gl][cl] = s2;
+  __syncthreads();
+  if (gl != 0 || c >= N) return;
+  s1 = 0.f;
+  s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s1 += sm[0][k][cl];
+    s2 += sm[1][k][cl];
   }
   sums[c] = s1;
   sums[ld + c] = s2;
@@ -594,17 +629,27 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict
     m1[k] = ok ? sums[c + k] * invB : 0.f;
     m2[k] = ok ? sums[ld + c + k] * invB : 0.f;
   }
-  for (int r = blockIdx.y; r < B; r += gridDim.y) {
-    const size_t o = static_cast<size_t>(r) * ld + c;
-    float d[8], z[8];
-    load8(dy_hi, dy_lo, o, d);
-    load8(z_hi, z_lo, o, z);
+  const int step = static_cast<int>(gridDim.y);
+  for (int r0 = blockIdx.y; r0 < B; r0 += 4 * step) {
+    float ds[4][8], zs[4][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (z[k] - mu[k]) * rs[k];
-      d[k] = (c + k < N) ? rs[k] * (d[k] - m1[k] - xh * m2[k]) : 0.f;
+    for (int u = 0; u < 4; ++u)  // eight independent 16-byte loads in flight
+      if (r0 + u * step < B) {
+        const size_t o = static_cast<size_t>(r0 + u * step) * ld + c;
+        load8(dy_hi, dy_lo, o, ds[u]);
+        load8(z_hi, z_lo, o, zs[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * step;
+      if (r >= B) break;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (zs[u][k] - mu[k]) * rs[k];
+        ds[u][k] = (c + k < N) ? rs[k] * (ds[u][k] - m1[k] - xh * m2[k]) : 0.f;
+      }
+      store8(dy_hi, dy_lo, static_cast<size_t>(r) * ld + c, ds[u]);
     }
-    store8(dy_hi, dy_lo, o, d);
   }
 }
 
@@ -921,7 +966,7 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
                     float* ws, float* sums, float* g_beta, cudaStream_t st) {
   dim3 grid((ld + 255) / 256, COLSUM_RS);
   bn_bwd_stage1_kernel<<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws);
-  bn_bwd_stage2_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, ld, N, sums, g_beta);
+  bn_bwd_stage2_kernel<<<(N + 31) / 32, 256, 0, st>>>(ws, ld, N, sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,

@@ -162,6 +162,14 @@ class Engine:
         self._check(self.lib.tfk_apply(self.h, float(lr), None, self._stream()))
         return None
 
+    def train_step(self, x, labels, lr, want_loss=True):
+        """accumulate + apply for one micro-batch with the Adam pass overlapped (tfk_train_step)"""
+        x, labels = self._dev_f32(x), self._dev_i32(labels)
+        out = C.c_float()
+        self._check(self.lib.tfk_train_step(self.h, _ptr(x), _ptr(labels), x.shape[0], float(lr),
+                                            C.byref(out) if want_loss else None, self._stream()))
+        return out.value if want_loss else None
+
     def eval_accumulate(self, x, labels):
         x, labels = self._dev_f32(x), self._dev_i32(labels)
         self._check(self.lib.tfk_eval_accumulate(self.h, _ptr(x), _ptr(labels), x.shape[0], self._stream()))

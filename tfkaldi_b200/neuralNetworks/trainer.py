@@ -216,6 +216,11 @@ class Trainer(object, metaclass=ABCMeta):
     def update(self, inputs, targets):
         """update the model with a batch: list of [T_u, I] matrices + list of [T_u] target vectors;
         returns the mean loss per frame evaluated before the update (trainer.py:260-354)"""
+        if len(inputs) == self.numutterances_per_minibatch:  # one micro-batch: fused accumulate+apply
+            k, x, y = self._stage(inputs, targets)
+            loss = self.engine.train_step(x, y, self.learning_rate_cached(), True)
+            self._stager.release(k)
+            return self._log(loss)
         for mats, tgts in self._microbatches(inputs, targets):
             k, x, y = self._stage(mats, tgts)
             self.engine.accumulate(x, y)
@@ -235,7 +240,7 @@ class Trainer(object, metaclass=ABCMeta):
         """fast path: one micro-batch already packed as x [B, I] float32 / y [B] int (pinned host tensors,
         numpy arrays or device tensors); same arithmetic as update()"""
         if isinstance(x, torch.Tensor) and x.is_cuda:
-            self.engine.accumulate(x, y)
+            return self._log(self.engine.train_step(x, y, self.learning_rate_cached(), want_loss))
         else:
             if self._stager is None:
                 self._stager = _Stager(self.engine.device, self.input_dim, self.max_frames)
@@ -250,11 +255,13 @@ class Trainer(object, metaclass=ABCMeta):
                 if isinstance(x, torch.Tensor):
                     x, y = x.numpy(), y.numpy()
                 k, dx, dy = self._stager.stage(x, y)
-            self.engine.accumulate(dx, dy)
+            if prefetch is not None:
+                # queue the next batch's H2D first (copy stream): it overlaps this whole step
+                self.prefetch(*prefetch)
+            # one micro-batch: fused step (per-layer Adam overlapped with the backward pass on one GPU)
+            loss = self.engine.train_step(dx, dy, self.learning_rate_cached(), want_loss)
             self._stager.release(k)
-        if prefetch is not None:
-            self.prefetch(*prefetch)  # next batch's H2D overlaps this step's kernels
-        return self._apply(want_loss)
+            return self._log(loss)
 
     def update_raw(self, raw_utts, cmvn_stats, targets, context_width):
         """update() from RAW features: list of un-normalised [T_u, D] matrices, their speakers' CMVN
@@ -282,10 +289,11 @@ class Trainer(object, metaclass=ABCMeta):
         return self._apply()
 
     def _apply(self, want_loss=True):
-        step = self.global_step if self.summarywriter is not None else None
-        loss = self.engine.apply(self.learning_rate_cached(), want_loss)
+        return self._log(self.engine.apply(self.learning_rate_cached(), want_loss))
+
+    def _log(self, loss):
         if self.summarywriter is not None and loss is not None:
-            self.summarywriter.write(json.dumps({"step": step, "loss": loss}) + "\n")
+            self.summarywriter.write(json.dumps({"step": self.global_step - 1, "loss": loss}) + "\n")
             self.summarywriter.flush()
         return loss
 
