@@ -191,13 +191,15 @@ int tfk_set_dropout_seed(tfk_handle* h, uint64_t seed);
  * every rank must call it, in the same order (checkpointing code that all ranks run does). */
 int tfk_comm_unique_id(uint8_t* id128_host);
 int tfk_comm_init(tfk_handle* h, const uint8_t* id128_host, int rank, int nranks);
-/* Fused reduce-scatter over NVLink peer memory (single node, after tfk_comm_init in the sharded mode):
- * every rank exports a 64-byte CUDA IPC handle of its gradient arena, the 64*nranks bytes of all
- * ranks (rank order) are imported by every rank.  From then on the wgrad kernel's epilogue
- * TMA-reduce-adds each output slab directly into the slice owner's accumulator (GEMM -> reduce-scatter
- * in one kernel); only layers whose rows split evenly over the ranks in multiples of 32 qualify, the
- * rest keep the NCCL reduce-scatter.  TFK_DP_MODE=sharded_nccl disables the fusion. */
-int tfk_ipc_export(tfk_handle* h, uint8_t* handle64_host);
+/* Collectives fused into the compute kernels over NVLink peer memory (single node, after tfk_comm_init in
+ * the sharded mode): every rank exports 256 bytes (four CUDA IPC handles: gradient arena, bf16 operand arenas
+ * hi / lo, publish flags); the 256*nranks bytes of all ranks (rank order) are imported by every rank.  Then
+ *   - GEMM -> reduce-scatter: the wgrad epilogue TMA-reduce-adds each output slab directly into the slice
+ *     owner's accumulator (layers whose rows split evenly over the ranks in multiples of 32; others keep NCCL);
+ *   - update -> all-gather: the sharded Adam kernel stores the refreshed bf16 operand slices into every peer's
+ *     arena as it computes them, followed by a flag publish/wait between the GPUs (no NCCL all-gather).
+ * TFK_DP_MODE=sharded_nccl disables both, fused_nccl_ag only the second. */
+int tfk_ipc_export(tfk_handle* h, uint8_t* handle256_host);
 int tfk_ipc_import(tfk_handle* h, const uint8_t* handles_host, int nranks);
 /* Alternative: adopt an existing ncclComm_t (not destroyed by tfk_destroy). */
 int tfk_set_comm(tfk_handle* h, void* nccl_comm, int rank, int nranks);

@@ -1,8 +1,9 @@
 """Data parallel on real GPUs (needs >= 2): K ranks, each feeding its own frames to tfk_accumulate and
 calling tfk_apply, must equal ONE GPU accumulating the same shards as micro-batches
 (trainer.py:310-332) — the semantics the reference has.  Three transports:
-  fused         wgrad epilogue TMA-reduce-adds into the owner GPU's slice over NVLink peer memory,
-                sharded Adam, bf16 all-gather (default on a single node)
+  fused         wgrad epilogue TMA-reduce-adds into the owner GPU's slice over NVLink peer memory, sharded Adam
+                that stores the refreshed bf16 operands into every peer + flag publish/wait (default on a node)
+  fused_nccl_ag the same with an NCCL all-gather of the operands
   sharded_nccl  NCCL reduce-scatter instead of the fused epilogue
   allreduce     NCCL all-reduce, replicated Adam"""
 import os
@@ -49,7 +50,7 @@ def _worker(rank, world, port, out_dir, mode):
     from tfkaldi_b200.engine import Engine
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    os.environ["TFK_DP_MODE"] = mode
+    os.environ["TFK_DP_MODE"] = "" if mode == "fused" else mode
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     eng = Engine(2, 440, 256, 183, 512, nonlin="linear", precision="bf16x3", device=rank)
@@ -66,7 +67,7 @@ def _worker(rank, world, port, out_dir, mode):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("mode", ["fused", "sharded_nccl", "allreduce"])
+@pytest.mark.parametrize("mode", ["fused", "fused_nccl_ag", "sharded_nccl", "allreduce"])
 def test_dp_equals_microbatch_accumulation(cuda_device, tmp_path, mode):
     import torch
     import torch.multiprocessing as mp

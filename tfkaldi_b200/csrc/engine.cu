@@ -112,6 +112,11 @@ struct tfk_handle {
   bool sharded = false;       // data parallel with reduce-scatter -> sharded Adam -> all-gather
   bool fused_rs = false;      // weight-gradient reduce-scatter fused into the wgrad epilogue (peer memory)
   std::vector<float*> peer_G; // [nranks] every rank's gradient arena (IPC-mapped; own pointer for self)
+  std::vector<__nv_bfloat16*> peer_Sh, peer_Sl;  // every rank's bf16 operand arenas
+  int* dp_flags = nullptr;                        // [256] published step per source rank (peers write here)
+  int** d_peer_flags = nullptr;                   // device array [nranks-1] of the OTHER ranks' flag arrays
+  bool fused_ag = false;                          // Adam stores the refreshed operands into every peer (no NCCL all-gather)
+  int dp_epoch = 0;
   std::vector<void*> ipc_opened;
   bool params_synced = true;  // fp32 master weights / Adam slots identical on every rank
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
@@ -858,6 +863,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
   CREATE_TRY(dev_alloc(h, &h->ws_colsum, 1024 + 64 * static_cast<size_t>(h->ldmax)));  // colsum counters + partials
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
+  CREATE_TRY(dev_alloc(h, &h->dp_flags, 256));
   {
     cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->acc_host), 2 * sizeof(double));
     if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "cudaMallocHost: %s", cudaGetErrorString(e)));
@@ -1172,8 +1178,14 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
     } else {
       off[0] = 0; cnt[0] = h->arena_n; n = 1;
     }
+    std::vector<__nv_bfloat16*> phi, plo;
+    if (h->sharded && h->fused_ag)
+      for (int r = 0; r < h->nranks; ++r)
+        if (r != h->rank) { phi.push_back(h->peer_Sh[r]); plo.push_back(h->peer_Sl[r]); }
+    // fused update -> all-gather: the weight slices (all segments but the last) are also stored into the peers
     TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, off, cnt, n, h->acc, lr_t,
-                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
+                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st, phi.empty() ? 0 : n - 1,
+                         static_cast<int>(phi.size()), phi.data(), h->x3 ? plo.data() : nullptr));
   }
   if (h->sharded) {
     // non-owned gradient slices still hold this rank's local sums: clear them for the next accumulation
@@ -1185,7 +1197,15 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
       if (lo + c < ly.w_count)
         TFK_CUDA(h, cudaMemsetAsync(h->G + ly.off_w + lo + c, 0, (ly.w_count - lo - c) * sizeof(float), st));
     }
-    TFK_TRY(all_gather_shadows(h, st));
+    if (h->fused_ag) {
+      // every rank has stored its refreshed operand slices into all peers: publish, then wait for the others
+      TimerScope ts(h, st, TFK_TIMER_ALLREDUCE, 2);
+      h->dp_epoch += 1;
+      TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, h->rank, h->dp_epoch, st));
+      TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, h->rank, h->dp_epoch, st));
+    } else {
+      TFK_TRY(all_gather_shadows(h, st));
+    }
     h->params_synced = false;
   }
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1392,13 +1412,18 @@ int tfk_set_comm(tfk_handle* h, void* nccl_comm, int rank, int nranks) {
   return nccl_comm ? setup_comm_streams(h) : TFK_OK;
 }
 
-int tfk_ipc_export(tfk_handle* h, uint8_t* handle64_host) {
-  if (!h || !handle64_host) return fail(h, TFK_EINVAL, "tfk_ipc_export: null argument");
+int tfk_ipc_export(tfk_handle* h, uint8_t* handle256_host) {
+  if (!h || !handle256_host) return fail(h, TFK_EINVAL, "tfk_ipc_export: null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
-  cudaIpcMemHandle_t hd;
-  TFK_CUDA(h, cudaIpcGetMemHandle(&hd, h->G));
-  memcpy(handle64_host, &hd, 64);
+  memset(handle256_host, 0, 256);
+  void* bufs[4] = {h->G, h->Sh, h->Sl, h->dp_flags};  // gradient arena, bf16 operand arenas, publish flags
+  for (int i = 0; i < 4; ++i) {
+    if (!bufs[i]) continue;
+    cudaIpcMemHandle_t hd;
+    TFK_CUDA(h, cudaIpcGetMemHandle(&hd, bufs[i]));
+    memcpy(handle256_host + 64 * i, &hd, 64);
+  }
   return TFK_OK;
 }
 
@@ -1407,15 +1432,29 @@ int tfk_ipc_import(tfk_handle* h, const uint8_t* handles_host, int nranks) {
   if (!h->sharded || nranks != h->nranks) return fail(h, TFK_EINVAL, "tfk_ipc_import: needs the sharded mode and %d handles", h->nranks);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
   h->peer_G.assign(nranks, nullptr);
+  h->peer_Sh.assign(nranks, nullptr);
+  h->peer_Sl.assign(nranks, nullptr);
+  std::vector<int*> peer_flags;
   for (int r = 0; r < nranks; ++r) {
-    if (r == h->rank) { h->peer_G[r] = h->G; continue; }
-    cudaIpcMemHandle_t hd;
-    memcpy(&hd, handles_host + 64 * r, 64);
-    void* p = nullptr;
-    TFK_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
-    h->ipc_opened.push_back(p);
-    h->peer_G[r] = static_cast<float*>(p);
+    if (r == h->rank) {
+      h->peer_G[r] = h->G; h->peer_Sh[r] = h->Sh; h->peer_Sl[r] = h->Sl;
+      continue;
+    }
+    void* mapped[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i) {
+      if (i == 2 && !h->x3) continue;
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, handles_host + 256 * r + 64 * i, 64);
+      TFK_CUDA(h, cudaIpcOpenMemHandle(&mapped[i], hd, cudaIpcMemLazyEnablePeerAccess));
+      h->ipc_opened.push_back(mapped[i]);
+    }
+    h->peer_G[r] = static_cast<float*>(mapped[0]);
+    h->peer_Sh[r] = static_cast<__nv_bfloat16*>(mapped[1]);
+    h->peer_Sl[r] = static_cast<__nv_bfloat16*>(mapped[2]);
+    peer_flags.push_back(static_cast<int*>(mapped[3]));
   }
+  if (!h->d_peer_flags) TFK_TRY(dev_alloc(h, &h->d_peer_flags, 256));
+  TFK_CUDA(h, cudaMemcpy(h->d_peer_flags, peer_flags.data(), peer_flags.size() * sizeof(int*), cudaMemcpyHostToDevice));
   // a layer is eligible when its rows split evenly over the ranks in multiples of the 32-row store slab
   int eligible = 0;
   for (int l = 0; l <= h->L; ++l) {
@@ -1425,7 +1464,9 @@ int tfk_ipc_import(tfk_handle* h, const uint8_t* handles_host, int nranks) {
     eligible += ly.peer_reduce ? 1 : 0;
   }
   const char* mode = getenv("TFK_DP_MODE");
-  h->fused_rs = eligible > 0 && !(mode && strcmp(mode, "sharded_nccl") == 0);
+  const bool nccl_only = mode && strcmp(mode, "sharded_nccl") == 0;
+  h->fused_rs = eligible > 0 && !nccl_only;
+  h->fused_ag = nranks <= 16 && !nccl_only && !(mode && strcmp(mode, "fused_nccl_ag") == 0);
   cudaDeviceSynchronize();
   for (auto& kv : h->plans) free_plan(kv.second);  // plans built before the import lack the peer maps
   h->plans.clear();

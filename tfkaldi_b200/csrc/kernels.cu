@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 
 #include <cfloat>
+#include <cstdio>
 
 #include "philox.cuh"
 
@@ -346,6 +347,11 @@ struct AdamSegs {
   unsigned long long off4[64];  // segment start, in float4 units
   unsigned long long cnt4[64];  // segment length, in float4 units
   int n;
+  // fused update -> all-gather: the refreshed bf16 operand copies of the first `n_bcast` segments are also
+  // stored into every peer GPU's shadow arena over NVLink (peer_hi[r] / peer_lo[r], r != self)
+  int n_bcast, n_peers;
+  uint2* peer_hi[15];
+  uint2* peer_lo[15];
 };
 // blockIdx.y = segment (the whole arena on one GPU; a rank's slice of every layer + the small
 // replicated region under sharded data parallelism)
@@ -382,7 +388,38 @@ adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__
     split2(wx[2], wx[3], h.y, l.y);
     w_hi[i] = h;
     if (w_lo) w_lo[i] = l;
+    if (static_cast<int>(blockIdx.y) < segs.n_bcast) {
+#pragma unroll 1
+      for (int r = 0; r < segs.n_peers; ++r) {
+        segs.peer_hi[r][i] = h;
+        if (w_lo) segs.peer_lo[r][i] = l;
+      }
+    }
   }
+  if (segs.n_bcast > 0) __threadfence_system();  // remote stores visible before the kernel is seen as done
+}
+
+// publish / wait: one flag word per source rank in every GPU's flag array (peer-mapped)
+__global__ void dp_publish_kernel(int* const* __restrict__ peer_flags, int n_peers, int me, int value) {
+  const int r = threadIdx.x;
+  if (r < n_peers) {
+    __threadfence_system();
+    *(reinterpret_cast<volatile int*>(peer_flags[r]) + me) = value;
+  }
+}
+__global__ void dp_wait_kernel(const int* __restrict__ flags, int n_ranks, int me, int value) {
+  const int r = threadIdx.x;
+  if (r < n_ranks && r != me) {
+    const volatile int* f = flags + r;
+    const long long t0 = clock64();
+    while (*f < value) {
+      if (clock64() - t0 > 6000000000LL) {
+        printf("tfk: timeout waiting for rank %d to publish step %d (have %d)\n", r, value, *f);
+        __trap();
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -915,10 +952,17 @@ int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, 
 
 int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, const size_t* seg_off,
            const size_t* seg_cnt, int nseg, const double* acc, float lr_t, float beta1, float beta2, float eps,
-           cudaStream_t st) {
+           cudaStream_t st, int n_bcast, int n_peers, __nv_bfloat16* const* peer_hi, __nv_bfloat16* const* peer_lo) {
   for (int s0 = 0; s0 < nseg; s0 += 64) {
     AdamSegs segs;
     segs.n = nseg - s0 < 64 ? nseg - s0 : 64;
+    segs.n_bcast = n_bcast - s0 > 0 ? (n_bcast - s0 < segs.n ? n_bcast - s0 : segs.n) : 0;
+    segs.n_peers = segs.n_bcast > 0 ? n_peers : 0;
+    if (segs.n_peers > 15) return static_cast<int>(cudaErrorInvalidValue);
+    for (int r = 0; r < segs.n_peers; ++r) {
+      segs.peer_hi[r] = reinterpret_cast<uint2*>(peer_hi[r]);
+      segs.peer_lo[r] = peer_lo ? reinterpret_cast<uint2*>(peer_lo[r]) : nullptr;
+    }
     size_t longest = 0;
     for (int i = 0; i < segs.n; ++i) {
       segs.off4[i] = seg_off[s0 + i] >> 2;
@@ -934,6 +978,15 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
                                       reinterpret_cast<uint2*>(w_hi), reinterpret_cast<uint2*>(w_lo), segs, acc, lr_t,
                                       beta1, beta2, eps);
   }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int k_dp_publish(int* const* d_peer_flags, int n_peers, int me, int value, cudaStream_t st) {
+  dp_publish_kernel<<<1, 32, 0, st>>>(d_peer_flags, n_peers, me, value);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_dp_wait(const int* flags, int n_ranks, int me, int value, cudaStream_t st) {
+  dp_wait_kernel<<<1, 32, 0, st>>>(flags, n_ranks, me, value);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -58,7 +58,14 @@ int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, 
 // one GPU, a rank's slice of every layer under sharded data parallelism.
 int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, const size_t* seg_off,
            const size_t* seg_cnt, int nseg, const double* acc, float lr_t, float beta1, float beta2, float eps,
-           cudaStream_t st);
+           cudaStream_t st, int n_bcast = 0, int n_peers = 0, __nv_bfloat16* const* peer_hi = nullptr,
+           __nv_bfloat16* const* peer_lo = nullptr);
+// Fused update -> all-gather (data parallel, peer memory): with n_bcast > 0 the refreshed bf16 copies of the
+// first n_bcast segments are ALSO stored into the n_peers other GPUs' shadow arenas (same offsets) over NVLink.
+// k_dp_publish then writes `value` into slot `me` of every peer's flag array (d_peer_flags: DEVICE array of
+// peer-mapped pointers); k_dp_wait spins until every other rank's slot in the local array reached `value`.
+int k_dp_publish(int* const* d_peer_flags, int n_peers, int me, int value, cudaStream_t st);
+int k_dp_wait(const int* flags, int n_ranks, int me, int value, cudaStream_t st);
 
 // Batch-norm (reference: classifiers/activation.py:159 -> tf.contrib.layers.batch_norm defaults):
 // finalize per-column batch statistics from the GEMM epilogue's 32-row partials, update the moving

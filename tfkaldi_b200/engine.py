@@ -241,13 +241,13 @@ class Engine:
         ident = (C.c_uint8 * 128).from_buffer_copy(payload[0])
         self._check(self.lib.tfk_comm_init(self.h, ident, rank, world))
         mode = os.environ.get("TFK_DP_MODE", "")
-        if mode not in ("allreduce", "sharded_nccl") and world & (world - 1) == 0:
+        if mode != "allreduce" and world & (world - 1) == 0:
             # single-node peer memory: let the wgrad epilogues reduce-add into the owners' accumulators
-            mine = (C.c_uint8 * 64)()
+            mine = (C.c_uint8 * 256)()
             self._check(self.lib.tfk_ipc_export(self.h, mine))
             handles = [None] * world
             dist.all_gather_object(handles, bytes(mine))
-            blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+            blob = (C.c_uint8 * (256 * world)).from_buffer_copy(b"".join(handles))
             self._check(self.lib.tfk_ipc_import(self.h, blob, world))
             dist.barrier()
 
