@@ -1,9 +1,9 @@
 // Persistent grouped tcgen05 GEMM with fused epilogues (see gemm.cuh for the role on the hot path).
 //
-// CTA = 192 threads, one CTA per SM (smem-limited):
+// CTA = 320 threads, one CTA per SM (smem-limited):
 //   warp 0   : tile scheduler + TMA producer (one elected lane)
 //   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane)
-//   warps 2-5: epilogue; warp w owns TMEM lanes / tile rows 32*(w%4) .. +31
+//   warps 2-9: epilogue; warp w owns TMEM lanes / tile rows 32*(w%4) .. +31 and half of the columns
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator ring full/empty (MMA <-> epilogue,
 // 2 x 256 columns so the next tile's MMAs overlap this tile's epilogue), tile-id ring (scheduler ->
 // MMA/epilogue; tiles are claimed with an atomic counter so long wgrad tiles and short dgrad tiles of
@@ -27,7 +27,7 @@ constexpr uint32_t B_TILE_BYTES = BN * BK * 2;  // 32 KB
 constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr uint32_t SLAB_BYTES = 32 * 128;  // 32 rows x 128 B, one epilogue warp's staging buffer
 constexpr uint32_t SLABS_OFF = STAGES * STAGE_BYTES;
-constexpr uint32_t BARS_OFF = SLABS_OFF + 4 * 2 * SLAB_BYTES;
+constexpr uint32_t BARS_OFF = SLABS_OFF + 8 * SLAB_BYTES;  // one slab per epilogue warp
 constexpr int SCHED_DEPTH = 4;
 constexpr uint32_t SMEM_USED = BARS_OFF + 256;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-byte alignment
@@ -99,12 +99,16 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue for one 128 x 256 accumulator tile, executed by the four epilogue warps.
+// Epilogue for one 128 x 256 accumulator tile.  Eight epilogue warps: warp w owns TMEM lanes / tile rows
+// 32*(w%4).. and the 32-column chunks [c_begin, c_end) (half of the tile each; a lone warp per scheduler
+// runs this dependent instruction stream at low IPC, two per scheduler nearly double the drain rate).
+// One 4 KB staging slab per warp (slab_a); the bf16x3 store needs two (hi, lo): there warps 2-5 do the whole
+// tile with their partner's slab as slab_b and warps 6-9 sit the tile out.
 // ------------------------------------------------------------------------------------------------
 template <int OUT>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tmem_acc, int m0,
-                                              int n0, uint32_t q, uint32_t lane, uint32_t slab_base,
-                                              int& sbuf) {
+                                              int n0, uint32_t q, uint32_t lane, uint32_t slab_a,
+                                              uint32_t slab_b, int c_begin, int c_end) {
   const int row = m0 + static_cast<int>(q * 32 + lane);
   const bool row_ok = row < pr.M;
   const uint32_t lane_taddr = tmem_acc + ((q * 32u) << 16);
@@ -112,7 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
   const uint32_t sw = lane & 7u;
 
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int col0 = n0 + c * 32;
     // bf16 outputs are emitted in 64-column groups (two chunks), fp32 outputs per 32-column chunk
     const int group_col0 = (OUT == OUT_BF16 || OUT == OUT_BF16_SPLIT) ? (n0 + (c & ~1) * 32) : col0;
@@ -242,9 +246,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     }
 
     if constexpr (OUT == OUT_F32 || OUT == OUT_F32_REDADD) {
-      if (lane == 0) tma_wait_group_read<1>();  // the slab written two stores ago is free again
+      if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the slab
       __syncwarp();
-      const uint32_t slab = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES + row_off;
+      const uint32_t slab = slab_a + row_off;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t addr = slab + ((static_cast<uint32_t>(j) ^ sw) << 4);
@@ -255,7 +259,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        const uint32_t src = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES;
+        const uint32_t src = slab_a;
         if constexpr (OUT == OUT_F32) {
           tma_store_2d(&pr.tmD[0], src, col0, m0 + static_cast<int>(q * 32));
         } else {
@@ -270,14 +274,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         }
         tma_commit_group();
       }
-      sbuf ^= 1;
     } else if constexpr (OUT == OUT_BF16) {
       const int half = c & 1;
       if (half == 0) {
-        if (lane == 0) tma_wait_group_read<1>();
+        if (lane == 0) tma_wait_group_read<0>();
         __syncwarp();
       }
-      const uint32_t slab = slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES + row_off;
+      const uint32_t slab = slab_a + row_off;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t addr = slab + ((static_cast<uint32_t>(half * 4 + j) ^ sw) << 4);
@@ -292,20 +295,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&pr.tmD[0], slab_base + static_cast<uint32_t>(sbuf) * SLAB_BYTES, group_col0,
-                       m0 + static_cast<int>(q * 32));
+          tma_store_2d(&pr.tmD[0], slab_a, group_col0, m0 + static_cast<int>(q * 32));
           tma_commit_group();
         }
-        sbuf ^= 1;
       }
-    } else {  // OUT_BF16_SPLIT: slab 0 = hi, slab 1 = lo
+    } else {  // OUT_BF16_SPLIT: slab_a = hi, slab_b = lo
       const int half = c & 1;
       if (half == 0) {
         if (lane == 0) tma_wait_group_read<0>();
         __syncwarp();
       }
-      const uint32_t slab_hi = slab_base + row_off;
-      const uint32_t slab_lo = slab_base + SLAB_BYTES + row_off;
+      const uint32_t slab_hi = slab_a + row_off;
+      const uint32_t slab_lo = slab_b + row_off;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t hi[4], lo[4];
@@ -332,13 +333,48 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&pr.tmD[0], slab_base, group_col0, m0 + static_cast<int>(q * 32));
-          tma_store_2d(&pr.tmD[1], slab_base + SLAB_BYTES, group_col0,
-                       m0 + static_cast<int>(q * 32));
+          tma_store_2d(&pr.tmD[0], slab_a, group_col0, m0 + static_cast<int>(q * 32));
+          tma_store_2d(&pr.tmD[1], slab_b, group_col0, m0 + static_cast<int>(q * 32));
           tma_commit_group();
         }
       }
     }
+  }
+}
+
+// Tile-level dispatch shared by both kernels.  `ew` = epilogue warp index 0..7.
+__device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_t tmem_acc, int m0, int n0,
+                                                  uint32_t ew, uint32_t lane, uint32_t slabs) {
+  // the hardware ties a warp to TMEM lanes 32 * (warp id % 4): epilogue warp ew is CTA warp ew + 2
+  const uint32_t q = (ew + 2) & 3, part = ew >> 2;
+  const uint32_t slab_a = slabs + ew * SLAB_BYTES;
+  if (pr.out_kind == OUT_BF16_SPLIT) {
+    // hi and lo need two slabs: warps 0-3 take the whole tile with their partner's (ew+4) slab; the pair
+    // meets on a named barrier afterwards so the partner never writes a slab that is still being read
+    if (part == 1) {  // entry: my slab may still be read by my previous (non-split) store
+      if (lane == 0) tma_wait_group_read<0>();
+      __syncwarp();
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    if (part == 0) {
+      epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_a, slab_a + 4 * SLAB_BYTES, 0, BN / 32);
+      if (lane == 0) tma_wait_group_read<0>();
+      __syncwarp();
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    return;
+  }
+  const int c0 = static_cast<int>(part) * (BN / 64), c1 = c0 + BN / 64;
+  switch (pr.out_kind) {
+    case OUT_BF16:
+      epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
+    case OUT_F32:
+      epilogue_tile<OUT_F32>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
+    default:
+      epilogue_tile<OUT_F32_REDADD>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
   }
 }
 
@@ -367,11 +403,11 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->tmem_full[i], 1);
-        mbar_init(&bars->tmem_empty[i], 4);
+        mbar_init(&bars->tmem_empty[i], 8);
       }
       for (int i = 0; i < SCHED_DEPTH; ++i) {
         mbar_init(&bars->sched_full[i], 1);
-        mbar_init(&bars->sched_empty[i], 5);  // MMA thread + 4 epilogue warps
+        mbar_init(&bars->sched_empty[i], 9);  // MMA thread + 8 epilogue warps
       }
       fence_mbar_init();
     }
@@ -489,9 +525,8 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
     }
   } else {
     // ============================ epilogue warps ============================
-    const uint32_t q = warp & 3;
-    const uint32_t slab_base = smem_base + SLABS_OFF + (warp - 2) * 2 * SLAB_BYTES;
-    int sbuf = 0, prev_split = 0;
+    const uint32_t ew = warp - 2;
+    const uint32_t slabs = smem_base + SLABS_OFF;
     for (int it = 0;; ++it) {
       const int slot = it % SCHED_DEPTH;
       mbar_wait(&bars->sched_full[slot], (it / SCHED_DEPTH) & 1);
@@ -505,30 +540,7 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + as * BN;
-      const int m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
-      // A split store reads BOTH slabs of this warp: drain before switching store discipline.
-      const int is_split = pr.out_kind == OUT_BF16_SPLIT;
-      if (is_split != prev_split) {
-        if (lane == 0) tma_wait_group_read<0>();
-        __syncwarp();
-        prev_split = is_split;
-        sbuf = 0;
-      }
-      switch (pr.out_kind) {
-        case OUT_BF16:
-          epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-          break;
-        case OUT_BF16_SPLIT:
-          epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-          break;
-        case OUT_F32:
-          epilogue_tile<OUT_F32>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-          break;
-        default:
-          epilogue_tile<OUT_F32_REDADD>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-          break;
-      }
+      epilogue_dispatch(pr, tmem_base + as * BN, tc.m_blk * BM, tc.n_blk * BN, ew, lane, slabs);
       // all tcgen05.ld of this accumulator are complete (tmem_ld_wait) -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -584,7 +596,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->tmem_full[i], 1);   // multicast tcgen05.commit from the leader
-        mbar_init(&bars->tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+        mbar_init(&bars->tmem_empty[i], 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
       }
       fence_mbar_init();
     }
@@ -682,9 +694,8 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
     }
   } else {
     // ============================ epilogue warps (both CTAs, own 128 rows) ============================
-    const uint32_t q = warp & 3;
-    const uint32_t slab_base = smem_base + SLABS_OFF + (warp - 2) * 2 * SLAB_BYTES;
-    int sbuf = 0, prev_split = 0;
+    const uint32_t ew = warp - 2;
+    const uint32_t slabs = smem_base + SLABS_OFF;
     for (int it = 0;; ++it) {
       const int tile = __ldg(my_list + it);
       if (tile < 0) break;
@@ -693,31 +704,9 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait_cluster(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + as * BN;
       const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN;
-      const int is_split = pr.out_kind == OUT_BF16_SPLIT;
-      if (is_split != prev_split) {
-        if (lane == 0) tma_wait_group_read<0>();
-        __syncwarp();
-        prev_split = is_split;
-        sbuf = 0;
-      }
-      if (m0 < pr.M) {  // a ragged last pair-tile may leave the peer CTA without rows
-        switch (pr.out_kind) {
-          case OUT_BF16:
-            epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-            break;
-          case OUT_BF16_SPLIT:
-            epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-            break;
-          case OUT_F32:
-            epilogue_tile<OUT_F32>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-            break;
-          default:
-            epilogue_tile<OUT_F32_REDADD>(pr, tmem_acc, m0, n0, q, lane, slab_base, sbuf);
-            break;
-        }
-      }
+      if (m0 < pr.M)  // a ragged last pair-tile may leave the peer CTA without rows (CTA-uniform)
+        epilogue_dispatch(pr, tmem_base + as * BN, m0, n0, ew, lane, slabs);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[as]);

@@ -20,7 +20,7 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;     // 2 accumulator stages x 256 fp32 columns
 
 enum OutKind : int {
