@@ -456,7 +456,7 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
 
 // backward of layer l given dZ_l (hidden: in dA[(L-1-l)&1], as d(loss)/d(layer OUTPUT after mask) for BN)
 int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
-                   const GemmParams* gemm_override = nullptr, bool fused_colsum = false) {
+                   const GemmParams* gemm_override = nullptr, bool fused_colsum = false, bool skip_colsum = false) {
   const int L = h->L;
   Layer& ly = h->layers[l];
   __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
@@ -475,7 +475,7 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
     TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
                                  ly.bn_sums, st));
   }
-  if (!fused_colsum || !ly.hidden || ly.bn || h->cfg.l2_norm) {
+  if (!skip_colsum && (!fused_colsum || !ly.hidden || ly.bn || h->cfg.l2_norm)) {
     TimerScope ts(h, st, TFK_TIMER_COLSUM);
     TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws_colsum, h->G + ly.off_b, st));
   }
@@ -1260,7 +1260,21 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
                          h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->adam_stream));
     return TFK_OK;
   };
-  TFK_TRY(backward_layer(h, *plan, B, h->L, st, nullptr, true));
+  // the colsum workspace has one user at a time: the side stream may take the output layer's column sums only when
+  // every hidden layer's bias gradient comes out of the fused GEMM epilogue (no BN / L2-norm reductions on `st`)
+  bool side_colsum = !h->cfg.l2_norm;
+  for (int l = 0; l < h->active; ++l) side_colsum = side_colsum && !h->layers[l].bn;
+  if (side_colsum) {
+    // the output layer's bias gradient (column sums of softmax - onehot) is only needed by the final small
+    // Adam launch: compute it on the side stream, concurrently with the backward GEMMs
+    TFK_CUDA(h, cudaEventRecord(h->layer_events[h->L + 1], st));
+    TFK_CUDA(h, cudaStreamWaitEvent(h->adam_stream, h->layer_events[h->L + 1], 0));
+    TimerScope ts(h, h->adam_stream, TFK_TIMER_COLSUM);
+    const Layer& lo = h->layers[h->L];
+    TFK_LAUNCH(h, k_colsum_bf16(h->dzo_hi, h->x3 ? h->dzo_lo : nullptr, h->ldo, B, lo.N, h->ws_colsum,
+                                h->G + lo.off_b, h->adam_stream));
+  }
+  TFK_TRY(backward_layer(h, *plan, B, h->L, st, nullptr, true, side_colsum));
   TFK_TRY(adam_layer(h->L));
   for (int l = h->active - 1; l >= 0; --l) {
     TFK_TRY(backward_layer(h, *plan, B, l, st, nullptr, true));
@@ -1281,6 +1295,9 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
       TFK_LAUNCH(h, k_colsum_finalize(parts, outs, n, (B + 31) / 32, h->ldh, h->cfg.hidden_dim, st));
     }
   }
+  // join the side stream (output-layer column sums, per-layer Adam launches) before the bias update
+  TFK_CUDA(h, cudaEventRecord(h->layer_events[h->L + 1], h->adam_stream));
+  TFK_CUDA(h, cudaStreamWaitEvent(st, h->layer_events[h->L + 1], 0));
   {  // biases / betas (small), then inactive layers' weight regions (zero gradients: a no-op update, kept for
      // exact equivalence with tfk_apply, which always covers the whole arena)
     TimerScope ts(h, st, TFK_TIMER_ADAM);
@@ -1291,8 +1308,6 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
     TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, off, cnt, n, h->acc, lr_t,
                          h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
   }
-  TFK_CUDA(h, cudaEventRecord(h->layer_events[h->L + 1], h->adam_stream));
-  TFK_CUDA(h, cudaStreamWaitEvent(st, h->layer_events[h->L + 1], 0));
   h->drop_seed += static_cast<unsigned long long>(h->L + 1);
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));

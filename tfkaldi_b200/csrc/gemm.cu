@@ -63,6 +63,11 @@ struct TileCoord {
   int kb_begin, kb_count;  // k-block range of this work item (split-K)
 };
 
+// tile-list entry of the CTA-pair kernel: tile index | (half << 28); half 0 = all 256 columns of the tile,
+// 1 / 2 = its left / right 128 columns (an M256 N128 MMA: same tensor throughput, half the time), -1 ends a list
+constexpr int kHalfShift = 28;
+constexpr int kTileMask = (1 << kHalfShift) - 1;
+
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
   TileCoord t;
   t.p = (P.nprob > 1 && tile >= P.p[1].tile_begin) ? 1 : 0;
@@ -344,7 +349,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
 
 // Tile-level dispatch shared by both kernels.  `ew` = epilogue warp index 0..7.
 __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_t tmem_acc, int m0, int n0,
-                                                  uint32_t ew, uint32_t lane, uint32_t slabs) {
+                                                  uint32_t ew, uint32_t lane, uint32_t slabs, int chunks = BN / 32) {
   // the hardware ties a warp to TMEM lanes 32 * (warp id % 4): epilogue warp ew is CTA warp ew + 2
   const uint32_t q = (ew + 2) & 3, part = ew >> 2;
   const uint32_t slab_a = slabs + ew * SLAB_BYTES;
@@ -357,14 +362,14 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_
     }
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
     if (part == 0) {
-      epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_a, slab_a + 4 * SLAB_BYTES, 0, BN / 32);
+      epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_a, slab_a + 4 * SLAB_BYTES, 0, chunks);
       if (lane == 0) tma_wait_group_read<0>();
       __syncwarp();
     }
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
     return;
   }
-  const int c0 = static_cast<int>(part) * (BN / 64), c1 = c0 + BN / 64;
+  const int c0 = static_cast<int>(part) * (chunks / 2), c1 = c0 + chunks / 2;  // chunks = 8 (256 cols) or 4 (half tile)
   switch (pr.out_kind) {
     case OUT_BF16:
       epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
@@ -614,17 +619,22 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int it = 0;; ++it) {
-        const int tile = __ldg(my_list + it);
-        if (tile < 0) break;
-        const TileCoord tc = decode_tile(P, tile);
+        const int entry = __ldg(my_list + it);
+        if (entry < 0) break;
+        const TileCoord tc = decode_tile(P, entry & kTileMask);
         const GemmProblem& pr = P.p[tc.p];
+        const int half = entry >> kHalfShift;  // 0: 256 columns, 1 / 2: left / right 128 columns
         const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128;  // this CTA's A / D rows
-        const int nb = tc.n_blk * BN + static_cast<int>(rank) * 128;   // this CTA's half of the B rows
+        // this CTA's half of the tile's B rows (128 of 256, or 64 of 128)
+        const int nb = tc.n_blk * BN + (half == 2 ? 128 : 0) + static_cast<int>(rank) * (half ? 64 : 128);
+        const int b_atoms = half ? 1 : 2;
+        // a K-major B box is always 128 rows (a half tile uses the first 64); MN-major B is loaded per 64-row atom
+        const uint32_t tx = 2 * (A_TILE_BYTES + (pr.b_mn ? b_atoms * MN_ATOM_BYTES : 2 * MN_ATOM_BYTES));
         const int iters = tc.kb_count * pr.nsplit;
         int kb = tc.kb_begin, s = 0;
         for (int i = 0; i < iters; ++i) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&bars->full[stage], 2 * STAGE2_BYTES);
+          if (rank == 0) mbar_expect_tx(&bars->full[stage], tx);
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
           const uint32_t sb = sa + A_TILE_BYTES;
           const CUtensorMap* ta = &pr.tmA[s == 2 ? 1 : 0];
@@ -638,8 +648,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
             tma_load_2d_2sm(sa, ta, &bars->full[stage], k0, m0);
           }
           if (pr.b_mn) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < b_atoms; ++j)
               tma_load_2d_2sm(sb + j * MN_ATOM_BYTES, tb, &bars->full[stage], nb + 64 * j, k0);
           } else {
             tma_load_2d_2sm(sb, tb, &bars->full[stage], k0, nb);
@@ -660,15 +669,15 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
       for (int it = 0;; ++it) {
-        const int tile = __ldg(my_list + it);
-        if (tile < 0) break;
-        const TileCoord tc = decode_tile(P, tile);
+        const int entry = __ldg(my_list + it);
+        if (entry < 0) break;
+        const TileCoord tc = decode_tile(P, entry & kTileMask);
         const GemmProblem& pr = P.p[tc.p];
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait_cluster(&bars->tmem_empty[as], aphase ^ 1);  // both CTAs' epilogues drained this stage
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * BN;
-        const uint32_t idesc = make_idesc_bf16(256, BN, pr.a_mn, pr.b_mn);
+        const uint32_t idesc = make_idesc_bf16(256, (entry >> kHalfShift) ? BN / 2 : BN, pr.a_mn, pr.b_mn);
         const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
         const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
         const int iters = tc.kb_count * pr.nsplit;
@@ -697,16 +706,17 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
     const uint32_t ew = warp - 2;
     const uint32_t slabs = smem_base + SLABS_OFF;
     for (int it = 0;; ++it) {
-      const int tile = __ldg(my_list + it);
-      if (tile < 0) break;
-      const TileCoord tc = decode_tile(P, tile);
+      const int entry = __ldg(my_list + it);
+      if (entry < 0) break;
+      const TileCoord tc = decode_tile(P, entry & kTileMask);
       const GemmProblem& pr = P.p[tc.p];
+      const int half = entry >> kHalfShift;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait_cluster(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN;
+      const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN + (half == 2 ? 128 : 0);
       if (m0 < pr.M)  // a ragged last pair-tile may leave the peer CTA without rows (CTA-uniform)
-        epilogue_dispatch(pr, tmem_base + as * BN, m0, n0, ew, lane, slabs);
+        epilogue_dispatch(pr, tmem_base + as * BN, m0, n0, ew, lane, slabs, half ? BN / 64 : BN / 32);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[as]);
@@ -940,29 +950,100 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
   if (!params->two_cta) return 0;
   const int total = params->total_tiles;
   int pairs = num_sms / 2;
-  if (pairs > total) pairs = total;
+  if (pairs > 2 * total) pairs = 2 * total;
   if (pairs < 1) pairs = 1;
-  // cost model: k-extent (MMA time) + a constant for the epilogue, in k-block units
-  std::vector<std::pair<long long, int>> order(total);
-  for (int t = 0; t < total; ++t) {
+  // Cost model, in half-k-block units: k-extent (MMA time) + a constant for the epilogue.  A tile may be scheduled
+  // as two 128-column halves (M256 N128 MMAs): used for tiles whose right half lies outside N, and where a launch
+  // has too few tiles to occupy every pair.
+  struct Item {
+    long long cost;
+    int entry;
+  };
+  std::vector<Item> full;   // tiles that may be scheduled whole or as two halves
+  std::vector<Item> fixed;  // tiles whose right 128 columns lie outside N: always a single left half
+  auto tile_cost = [&](int t, bool half) -> long long {
     const int pi = (params->nprob > 1 && t >= params->p[1].tile_begin) ? 1 : 0;
     const GemmProblem& pr = params->p[pi];
     const int local = t - pr.tile_begin;
     const int split = local / (pr.tiles_m * pr.tiles_n);
     const int kb0 = split * pr.kb_per_split;
     const int cnt = pr.kb_per_split < pr.num_kb - kb0 ? pr.kb_per_split : pr.num_kb - kb0;
-    order[t] = {static_cast<long long>(cnt) * pr.nsplit + 6, t};
+    const long long mma = static_cast<long long>(cnt) * pr.nsplit;
+    // measured: a half tile takes ~3/4 of a whole one (the mainloop is paced by operand delivery, and a half tile
+    // still stages all of A), so halving only pays where it buys parallelism, not for evening out the last round
+    return half ? (3 * mma) / 2 + 9 : 2 * mma + 12;
+  };
+  for (int t = 0; t < total; ++t) {
+    const int pi = (params->nprob > 1 && t >= params->p[1].tile_begin) ? 1 : 0;
+    const GemmProblem& pr = params->p[pi];
+    const int n_blk = (t - pr.tile_begin) % pr.tiles_n;
+    if (n_blk * BN + BN / 2 >= pr.N)
+      fixed.push_back({tile_cost(t, true), t | (1 << kHalfShift)});
+    else
+      full.push_back({tile_cost(t, false), t});
   }
-  std::stable_sort(order.begin(), order.end(),
-                   [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first > b.first; });
-  std::vector<std::vector<int>> lists(pairs);
-  std::vector<long long> load(pairs, 0);
-  for (const auto& it : order) {
-    int best = 0;
-    for (int p = 1; p < pairs; ++p)
-      if (load[p] < load[best]) best = p;
-    lists[best].push_back(it.second);
-    load[best] += it.first;
+  auto by_cost = [](const Item& a, const Item& b) { return a.cost > b.cost; };
+  std::stable_sort(full.begin(), full.end(), by_cost);
+  // longest-processing-time-first assignment of `items`; returns the makespan
+  auto lpt = [&](std::vector<Item> items, std::vector<std::vector<int>>* lists) -> long long {
+    std::stable_sort(items.begin(), items.end(), by_cost);
+    std::vector<long long> load(pairs, 0);
+    if (lists) lists->assign(pairs, std::vector<int>());
+    for (const auto& it : items) {
+      int best = 0;
+      for (int p = 1; p < pairs; ++p)
+        if (load[p] < load[best]) best = p;
+      if (lists) (*lists)[best].push_back(it.entry);
+      load[best] += it.cost;
+    }
+    long long mk = 0;
+    for (long long l : load) mk = l > mk ? l : mk;
+    return mk;
+  };
+  auto with_split = [&](int nsplit_tiles) {  // the `nsplit_tiles` cheapest whole tiles become two halves each
+    std::vector<Item> items(fixed);
+    const int nfull = static_cast<int>(full.size());
+    for (int i = 0; i < nfull; ++i) {
+      const int t = full[i].entry;
+      if (i >= nfull - nsplit_tiles) {
+        const long long c = tile_cost(t, true);
+        items.push_back({c, t | (1 << kHalfShift)});
+        items.push_back({c, t | (2 << kHalfShift)});
+      } else {
+        items.push_back(full[i]);
+      }
+    }
+    return items;
+  };
+  int best_split = 0;
+  {
+    const char* force = getenv("TFK_GEMM_HALF_TILES");  // "all": every tile as halves (tests); "0": never
+    const int nfull = static_cast<int>(full.size());
+    if (force && strcmp(force, "all") == 0) {
+      best_split = nfull;
+    } else if (!(force && strcmp(force, "0") == 0)) {
+      const long long whole = lpt(with_split(0), nullptr);
+      long long best = whole - whole / 10;  // accept a split only for a modelled gain of 10 % or more
+      const int limit = nfull < 2 * pairs ? nfull : 2 * pairs;
+      for (int sp = 1; sp <= limit; ++sp) {
+        const long long mk = lpt(with_split(sp), nullptr);
+        if (mk < best) {
+          best = mk;
+          best_split = sp;
+        }
+      }
+    }
+  }
+  std::vector<std::vector<int>> lists;
+  lpt(with_split(best_split), &lists);
+  if (static_cast<int>(fixed.size()) + static_cast<int>(full.size()) + best_split < pairs) {
+    // fewer work items than pairs: launch only the pairs that got one
+    int used = 0;
+    for (const auto& l : lists) used += l.empty() ? 0 : 1;
+    std::stable_sort(lists.begin(), lists.end(),
+                     [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+    pairs = used < 1 ? 1 : used;
+    lists.resize(pairs);
   }
   size_t stride = 1;
   for (const auto& l : lists) stride = l.size() + 1 > stride ? l.size() + 1 : stride;
