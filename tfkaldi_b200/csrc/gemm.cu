@@ -953,12 +953,15 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
   if (pairs > 2 * total) pairs = 2 * total;
   if (pairs < 1) pairs = 1;
   // Cost model, in half-k-block units: k-extent (MMA time) + a constant for the epilogue.  A tile may be scheduled
-  // as two 128-column halves (M256 N128 MMAs): used for tiles whose right half lies outside N, and where a launch
-  // has too few tiles to occupy every pair.
+  // as two 128-column halves (M256 N128 MMAs): used for tiles whose right half lies outside N, to shorten a partly
+  // filled last round (256 equal tiles on 74 pairs: 3 + 0.8 rounds instead of 4) and for launches with few tiles.
   struct Item {
     long long cost;
     int entry;
   };
+  const char* force = getenv("TFK_GEMM_HALF_TILES");  // "all": every tile as halves (tests); "0": never;
+                                                      // "auto": halves cost half, any modelled gain is taken
+  const bool optimistic = force && strcmp(force, "auto") == 0;
   std::vector<Item> full;   // tiles that may be scheduled whole or as two halves
   std::vector<Item> fixed;  // tiles whose right 128 columns lie outside N: always a single left half
   auto tile_cost = [&](int t, bool half) -> long long {
@@ -969,9 +972,10 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
     const int kb0 = split * pr.kb_per_split;
     const int cnt = pr.kb_per_split < pr.num_kb - kb0 ? pr.kb_per_split : pr.num_kb - kb0;
     const long long mma = static_cast<long long>(cnt) * pr.nsplit;
-    // measured: a half tile takes ~3/4 of a whole one (the mainloop is paced by operand delivery, and a half tile
-    // still stages all of A), so halving only pays where it buys parallelism, not for evening out the last round
-    return half ? (3 * mma) / 2 + 9 : 2 * mma + 12;
+    // measured (profiles/r1_halftile_policies.txt): a half tile takes 0.8 of a whole one, not 0.5 - the mainloop is
+    // paced by operand delivery from L2 (~70 GB/s per SM) and a half tile still stages all of A
+    if (optimistic) return half ? mma + 7 : 2 * mma + 12;
+    return half ? (8 * (2 * mma + 12)) / 10 : 2 * mma + 12;
   };
   for (int t = 0; t < total; ++t) {
     const int pi = (params->nprob > 1 && t >= params->p[1].tile_begin) ? 1 : 0;
@@ -1017,13 +1021,12 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
   };
   int best_split = 0;
   {
-    const char* force = getenv("TFK_GEMM_HALF_TILES");  // "all": every tile as halves (tests); "0": never
     const int nfull = static_cast<int>(full.size());
     if (force && strcmp(force, "all") == 0) {
       best_split = nfull;
     } else if (!(force && strcmp(force, "0") == 0)) {
       const long long whole = lpt(with_split(0), nullptr);
-      long long best = whole - whole / 10;  // accept a split only for a modelled gain of 10 % or more
+      long long best = optimistic ? whole : whole - whole / 50;  // default: only for a modelled gain of 2 % or more
       const int limit = nfull < 2 * pairs ? nfull : 2 * pairs;
       for (int sp = 1; sp <= limit; ++sp) {
         const long long mk = lpt(with_split(sp), nullptr);
@@ -1035,7 +1038,10 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
     }
   }
   std::vector<std::vector<int>> lists;
-  lpt(with_split(best_split), &lists);
+  const long long makespan = lpt(with_split(best_split), &lists);
+  if (getenv("TFK_GEMM_DEBUG"))
+    fprintf(stderr, "[tfk gemm] %d tiles (%zu left-half only), %d pairs: %d tiles split in two, modelled makespan %lld\n",
+            total, fixed.size(), pairs, best_split, makespan);
   if (static_cast<int>(fixed.size()) + static_cast<int>(full.size()) + best_split < pairs) {
     // fewer work items than pairs: launch only the pairs that got one
     int used = 0;
