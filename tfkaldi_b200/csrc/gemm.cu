@@ -585,6 +585,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
   const uint32_t rank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
   const int* __restrict__ my_list = P.tile_list + static_cast<size_t>(pair) * P.list_stride;
+  pdl_launch_dependents();  // the next kernel in the stream may set itself up as soon as SMs free up
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < P.nprob; ++p) {
@@ -613,6 +614,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ============================ TMA producer (both CTAs) ============================
@@ -937,8 +939,21 @@ int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream) {
   if (rc) return rc;
   if (params.two_cta) {
     if (params.tile_list == nullptr || params.num_pairs < 1) return (int)cudaErrorInvalidValue;
-    tfk_gemm2_kernel<<<2 * params.num_pairs, GEMM_THREADS, SMEM_BYTES, stream>>>(params);
-    return (int)cudaGetLastError();
+    static const bool pdl = [] {
+      const char* e = getenv("TFK_PDL");
+      return !(e && e[0] == '0');
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * params.num_pairs, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, tfk_gemm2_kernel, params);
   }
   const int grid = params.total_tiles < num_sms ? params.total_tiles : num_sms;
   tfk_gemm_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(params);
