@@ -249,7 +249,7 @@ def run_ours(args):
                          "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
                          "peak_source": peaks["source"] + " (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
-                         "algorithmic_flops_per_step": train_fl * B, "kernel_ms_per_step": gemm_ms, "traffic": None,
+                         "algorithmic_flops_per_step": train_fl * B, "kernel_ms_per_step": gemm_ms, **_ncu_traffic(args, B),
                          "step_share": gemm_ms / ms_resident, "per_step_us_by_kernel_class": breakdown},
             "hbm_kernels": hbm,
             "clocks": clocks,
@@ -261,6 +261,20 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def _ncu_traffic(args, frames):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this exact
+    workload (profiles/r1_ncu_traffic.json); null for workloads that were not captured."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_traffic.json")
+    try:
+        t = json.load(open(path)).get("%s:%s:%d" % (args.config, args.precision, frames))
+    except (OSError, ValueError):
+        t = None
+    if not t:
+        return {"traffic": None}
+    return {"traffic": t["dram_bytes_per_launch"], "traffic_unit": "bytes of DRAM read+write per launch (mean of the %d launches of a step)" % t["launches_per_step"],
+            "traffic_source": t["source"]}
 
 
 _THREADS = {}
