@@ -132,6 +132,7 @@ struct tfk_handle {
   float *bn_ps = nullptr, *bn_pq = nullptr;
   float* ws = nullptr;
   float* ws_colsum = nullptr;
+  unsigned int* bn_counters = nullptr;  // 512 self-resetting counters of the BN backward reduction
   float* tmp_f32 = nullptr;
   int* sched = nullptr;
   std::map<long long, Plan> plans;
@@ -146,6 +147,7 @@ struct tfk_handle {
   cudaStream_t comm_stream = nullptr;
   cudaStream_t adam_stream = nullptr;      // tfk_train_step: per-layer Adam overlapped with the rest of the backward pass
   std::vector<cudaEvent_t> layer_events;
+  std::vector<cudaEvent_t> colsum_events;  // tfk_train_step: column sums of layer l taken (side stream)
   int pending_accumulates = 0;             // tfk_accumulate calls since the last tfk_apply
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   // timers
@@ -455,8 +457,10 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
 }
 
 // backward of layer l given dZ_l (hidden: in dA[(L-1-l)&1], as d(loss)/d(layer OUTPUT after mask) for BN)
+// `side`: tfk_train_step's second stream.  Bias-gradient column sums that need their own kernel are only consumed by
+// the final bias update, so they run there, next to the backward GEMM, fenced by per-layer events.
 int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
-                   const GemmParams* gemm_override = nullptr, bool fused_colsum = false, bool skip_colsum = false) {
+                   const GemmParams* gemm_override = nullptr, bool fused_colsum = false, cudaStream_t side = nullptr) {
   const int L = h->L;
   Layer& ly = h->layers[l];
   __nv_bfloat16* dz_hi = ly.hidden ? h->dA_hi[(L - 1 - l) & 1] : h->dzo_hi;
@@ -471,14 +475,24 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
   if (ly.hidden && ly.bn) {  // d(bn output) -> d(linear output), plus dbeta
     TimerScope ts(h, st, TFK_TIMER_BN, 3);
     TFK_LAUNCH(h, k_bn_bwd_reduce(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
-                                  h->ws, ly.bn_sums, h->G + ly.off_beta, st));
+                                  h->ws, h->bn_counters, ly.bn_sums, h->G + ly.off_beta, st));
     TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
                                  ly.bn_sums, st));
   }
-  if (!skip_colsum && (!fused_colsum || !ly.hidden || ly.bn || h->cfg.l2_norm)) {
-    TimerScope ts(h, st, TFK_TIMER_COLSUM);
-    TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws_colsum, h->G + ly.off_b, st));
+  if (!fused_colsum || !ly.hidden || ly.bn || h->cfg.l2_norm) {
+    cudaStream_t cs = side ? side : st;
+    if (side) {  // dZ_l is final on `st` here
+      TFK_CUDA(h, cudaEventRecord(h->colsum_events[l], st));
+      TFK_CUDA(h, cudaStreamWaitEvent(side, h->colsum_events[l], 0));
+    }
+    {
+      TimerScope ts(h, cs, TFK_TIMER_COLSUM);
+      TFK_LAUNCH(h, k_colsum_bf16(dz_hi, dz_lo, ldz, B, ly.N, h->ws_colsum, h->G + ly.off_b, cs));
+    }
+    if (side) TFK_CUDA(h, cudaEventRecord(h->colsum_events[l], side));
   }
+  // this layer's GEMM writes dZ_{l-1} into the buffer that held dZ_{l+1}: its column sums must have been taken
+  if (side && l + 1 < L) TFK_CUDA(h, cudaStreamWaitEvent(st, h->colsum_events[l + 1], 0));
   {
     TimerScope ts(h, st, TFK_TIMER_GEMM_BWD);
     TFK_LAUNCH(h, gemm_launch(gemm_override ? *gemm_override : plan.bwd[l], h->num_sms, st));
@@ -713,6 +727,7 @@ int tfk_destroy(tfk_handle* h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->adam_stream) cudaStreamDestroy(h->adam_stream);
   for (auto e : h->layer_events) cudaEventDestroy(e);
+  for (auto e : h->colsum_events) cudaEventDestroy(e);
   for (auto& kv : h->plans) free_plan(kv.second);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->allocs) cudaFree(p);
@@ -861,6 +876,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
   }
   CREATE_TRY(dev_alloc(h, &h->ws, 256 * static_cast<size_t>(h->ldmax)));       // bn backward partials [128][2][ld]
   CREATE_TRY(dev_alloc(h, &h->ws_colsum, 1024 + 64 * static_cast<size_t>(h->ldmax)));  // colsum counters + partials
+  CREATE_TRY(dev_alloc(h, &h->bn_counters, 512));
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
   CREATE_TRY(dev_alloc(h, &h->dp_flags, 256));
@@ -1235,6 +1251,8 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
     TFK_CUDA(h, cudaStreamCreateWithFlags(&h->adam_stream, cudaStreamNonBlocking));
     h->layer_events.resize(h->L + 2);
     for (auto& e : h->layer_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->colsum_events.resize(h->L + 1);
+    for (auto& e : h->colsum_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   Plan* plan;
   TFK_TRY(get_plan(h, B, &plan));
@@ -1260,24 +1278,12 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
                          h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->adam_stream));
     return TFK_OK;
   };
-  // the colsum workspace has one user at a time: the side stream may take the output layer's column sums only when
-  // every hidden layer's bias gradient comes out of the fused GEMM epilogue (no BN / L2-norm reductions on `st`)
-  bool side_colsum = !h->cfg.l2_norm;
-  for (int l = 0; l < h->active; ++l) side_colsum = side_colsum && !h->layers[l].bn;
-  if (side_colsum) {
-    // the output layer's bias gradient (column sums of softmax - onehot) is only needed by the final small
-    // Adam launch: compute it on the side stream, concurrently with the backward GEMMs
-    TFK_CUDA(h, cudaEventRecord(h->layer_events[h->L + 1], st));
-    TFK_CUDA(h, cudaStreamWaitEvent(h->adam_stream, h->layer_events[h->L + 1], 0));
-    TimerScope ts(h, h->adam_stream, TFK_TIMER_COLSUM);
-    const Layer& lo = h->layers[h->L];
-    TFK_LAUNCH(h, k_colsum_bf16(h->dzo_hi, h->x3 ? h->dzo_lo : nullptr, h->ldo, B, lo.N, h->ws_colsum,
-                                h->G + lo.off_b, h->adam_stream));
-  }
-  TFK_TRY(backward_layer(h, *plan, B, h->L, st, nullptr, true, side_colsum));
+  // bias-gradient column sums that are not produced by a GEMM epilogue (output layer; BN / L2Norm layers) go to the
+  // side stream: they are only needed by the final small Adam launch
+  TFK_TRY(backward_layer(h, *plan, B, h->L, st, nullptr, true, h->adam_stream));
   TFK_TRY(adam_layer(h->L));
   for (int l = h->active - 1; l >= 0; --l) {
-    TFK_TRY(backward_layer(h, *plan, B, l, st, nullptr, true));
+    TFK_TRY(backward_layer(h, *plan, B, l, st, nullptr, true, h->adam_stream));
     TFK_TRY(adam_layer(l));
   }
   {

@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(1024) accum_loss_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int COLSUM_RS = 128;  // row splits of the BN-backward reductions
 constexpr int COLSUM2_RS = 64;  // row splits of colsum_kernel
 // Single launch, deterministic.  A warp reads 256 consecutive columns (16 B per lane) of one row per
 // load; a block's 8 warps stride over its row range; the LAST block to finish a 256-column group adds
@@ -510,71 +509,132 @@ __device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, siz
   if (lo) *reinterpret_cast<uint4*>(lo + o) = l;
 }
 
-// thread = one 8-column group (its mean / rstd / beta live in registers); blockIdx.y strides over the rows
-__global__ void __launch_bounds__(256)
+// Raw 16-byte row fragments (bf16 hi [+ lo]) are kept in flight as loaded; converted only when consumed.
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, bool has_lo, float (&x)[8]) {
+  x[0] = bf_lo(h.x); x[1] = bf_hi(h.x); x[2] = bf_lo(h.y); x[3] = bf_hi(h.y);
+  x[4] = bf_lo(h.z); x[5] = bf_hi(h.z); x[6] = bf_lo(h.w); x[7] = bf_hi(h.w);
+  if (has_lo) {
+    x[0] += bf_lo(l.x); x[1] += bf_hi(l.x); x[2] += bf_lo(l.y); x[3] += bf_hi(l.y);
+    x[4] += bf_lo(l.z); x[5] += bf_hi(l.z); x[6] += bf_lo(l.w); x[7] += bf_hi(l.w);
+  }
+}
+
+constexpr int BN_SPAN = 2048;  // columns per block of the element-wise BN kernels (256 threads x 8)
+constexpr int BN_ROWS = 4;     // rows in flight per thread
+
+// Block = a 2048-column span x a strided set of rows; thread = 8 columns, BN_ROWS rows in flight (raw 16-byte
+// fragments, transformed in place word by word).  A thread's per-column vectors are parked in shared memory
+// ([column-in-thread][thread]: conflict-free, private to the thread, so no barrier) instead of 24-32 registers and
+// fetched four columns at a time for all rows in flight.  Four blocks per SM; the grid is exactly one wave.
+template <bool X3>
+__global__ void __launch_bounds__(256, 4)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
                 int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ beta, int relu, unsigned int drop_thr, float keep_inv,
                 unsigned long long seed, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
+  __shared__ float s_mu[8][256], s_rs[8][256], s_be[8][256];
+  const int cb = blockIdx.x * BN_SPAN;
+  const int t = threadIdx.x;
+  const int c = cb + (t << 3);
   if (c >= ld) return;
-  float mu[8], rs[8], be[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < 8; ++k) {  // each thread stages its own eight columns: no barrier, conflict-free stores
     const bool ok = c + k < N;
-    mu[k] = ok ? mean[c + k] : 0.f;
-    rs[k] = ok ? rstd[c + k] : 0.f;
-    be[k] = ok ? beta[c + k] : 0.f;
+    s_mu[k][t] = ok ? __ldg(mean + c + k) : 0.f;
+    s_rs[k][t] = ok ? __ldg(rstd + c + k) : 0.f;
+    s_be[k][t] = ok ? __ldg(beta + c + k) : 0.f;
   }
   const int step = static_cast<int>(gridDim.y);
-  for (int r0 = blockIdx.y; r0 < B; r0 += 4 * step) {
-    float xs[4][8];
+  for (int r0 = blockIdx.y; r0 < B; r0 += BN_ROWS * step) {
+    uint32_t hw[BN_ROWS][4], lw[BN_ROWS][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)  // four rows' loads in flight before any arithmetic
-      if (r0 + u * step < B) load8(z_hi, z_lo, static_cast<size_t>(r0 + u * step) * ld + c, xs[u]);
+    for (int u = 0; u < BN_ROWS; ++u)
+      if (r0 + u * step < B) {
+        const size_t o = static_cast<size_t>(r0 + u * step) * ld + c;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+        hw[u][0] = h.x; hw[u][1] = h.y; hw[u][2] = h.z; hw[u][3] = h.w;
+        if (X3) {
+          const uint4 l = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+          lw[u][0] = l.x; lw[u][1] = l.y; lw[u][2] = l.z; lw[u][3] = l.w;
+        }
+      }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-    const int r = r0 + u * step;
-    if (r >= B) break;
-    const size_t o = static_cast<size_t>(r) * ld + c;
-    float (&x)[8] = xs[u];
+    for (int jj = 0; jj < 2; ++jj) {  // columns c + 4 jj .. c + 4 jj + 3
+      float mu[4], rs[4], be[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float y = (x[k] - mu[k]) * rs[k] + be[k];
-      if (relu == 1) y = fmaxf(y, 0.f);
-      else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
-      else if (relu == 3) y = tanhf(y);
-      x[k] = (c + k < N) ? y : 0.f;
-    }
-    if (drop_thr != 0u) {
+      for (int i = 0; i < 4; ++i) {
+        mu[i] = s_mu[4 * jj + i][t];
+        rs[i] = s_rs[4 * jj + i][t];
+        be[i] = s_be[4 * jj + i][t];
+      }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(c >> 2) + j, static_cast<uint32_t>(r), 0u, 0u,
-                                          static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-        x[4 * j + 0] = ((rnd.x >> 8) >= drop_thr) ? x[4 * j + 0] * keep_inv : 0.f;
-        x[4 * j + 1] = ((rnd.y >> 8) >= drop_thr) ? x[4 * j + 1] * keep_inv : 0.f;
-        x[4 * j + 2] = ((rnd.z >> 8) >= drop_thr) ? x[4 * j + 2] * keep_inv : 0.f;
-        x[4 * j + 3] = ((rnd.w >> 8) >= drop_thr) ? x[4 * j + 3] * keep_inv : 0.f;
+      for (int u = 0; u < BN_ROWS; ++u) {
+        const int r = r0 + u * step;
+        if (r < B) {
+          float keepf[4] = {1.f, 1.f, 1.f, 1.f};
+          if (drop_thr != 0u) {
+            const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(c >> 2) + jj, static_cast<uint32_t>(r), 0u, 0u,
+                                              static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+            keepf[0] = ((rnd.x >> 8) >= drop_thr) ? keep_inv : 0.f;
+            keepf[1] = ((rnd.y >> 8) >= drop_thr) ? keep_inv : 0.f;
+            keepf[2] = ((rnd.z >> 8) >= drop_thr) ? keep_inv : 0.f;
+            keepf[3] = ((rnd.w >> 8) >= drop_thr) ? keep_inv : 0.f;
+          }
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int j = 2 * jj + w;
+            float x[2] = {bf_lo(hw[u][j]), bf_hi(hw[u][j])};
+            if (X3) {
+              x[0] += bf_lo(lw[u][j]);
+              x[1] += bf_hi(lw[u][j]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = 2 * w + e;
+              float y = (x[e] - mu[i]) * rs[i] + be[i];
+              if (relu == 1) y = fmaxf(y, 0.f);
+              else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
+              else if (relu == 3) y = tanhf(y);
+              y = (c + 4 * jj + i < N) ? y : 0.f;
+              x[e] = (drop_thr != 0u) ? ((keepf[i] != 0.f) ? y * keepf[i] : 0.f) : y;
+            }
+            split2(x[0], x[1], hw[u][j], lw[u][j]);
+          }
+        }
       }
     }
-    store8(y_hi, y_lo, o, x);
+#pragma unroll
+    for (int u = 0; u < BN_ROWS; ++u) {
+      const int r = r0 + u * step;
+      if (r < B) {
+        const size_t o = static_cast<size_t>(r) * ld + c;
+        *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hw[u][0], hw[u][1], hw[u][2], hw[u][3]);
+        if (X3) *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lw[u][0], lw[u][1], lw[u][2], lw[u][3]);
+      }
     }
   }
 }
 
-// stage 1 of the BN backward column reductions; ws layout [RS][2][ld].  A warp reads 256 consecutive
-// columns (16 B per lane per array) of one row per load; 8 warps stride over the block's row range.
-__global__ void __launch_bounds__(256)
-bn_bwd_stage1_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat16* __restrict__ dy_lo,
+// BN backward column reductions sum_B(dy) and sum_B(dy * xhat), one launch, deterministic.  ws layout [RS][2][ld].
+// A warp reads 256 consecutive columns (16 B per lane per array) of one row per load; a block's 8 warps stride over
+// its row range; the LAST block to finish a 256-column group adds the BN_RS partials in fixed order
+// (threadfence + self-resetting counter) into sums[] and the beta gradient.  grid = (ld/256, 74): one wave.
+constexpr int BN_RS = 74;
+template <bool X3>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat16* __restrict__ dy_lo,
                      const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
                      int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     float* __restrict__ ws) {
+                     float* __restrict__ ws, unsigned int* __restrict__ counters, float* __restrict__ sums,
+                     float* __restrict__ g_beta) {
   __shared__ float sm[8][256];
+  __shared__ unsigned int last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   const int rs = blockIdx.y;
-  const int per = (B + COLSUM_RS - 1) / COLSUM_RS;
+  const int per = (B + BN_RS - 1) / BN_RS;
   const int r0 = rs * per, r1 = min(B, r0 + per);
+  constexpr bool has_lo = X3;
   float a[8], b[8], mu[8], rsd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -584,19 +644,35 @@ bn_bwd_stage1_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat1
     rsd[k] = (col + k < N) ? rstd[col + k] : 0.f;
   }
   if (col < ld) {
-#pragma unroll 2
-    for (int r = r0 + w; r < r1; r += 8) {
-      const size_t o = static_cast<size_t>(r) * ld + col;
-      float d[8], z[8];
-      load8(dy_hi, dy_lo, o, d);
-      load8(z_hi, z_lo, o, z);
+    for (int r = r0 + w; r < r1; r += 16) {  // two rows x two arrays in flight
+      uint4 dh[2], dl[2], zh[2], zl[2];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a[k] += d[k];
-        b[k] += d[k] * ((z[k] - mu[k]) * rsd[k]);
-      }
+      for (int u = 0; u < 2; ++u)
+        if (r + 8 * u < r1) {
+          const size_t o = static_cast<size_t>(r + 8 * u) * ld + col;
+          dh[u] = __ldg(reinterpret_cast<const uint4*>(dy_hi + o));
+          zh[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+          if (has_lo) {
+            dl[u] = __ldg(reinterpret_cast<const uint4*>(dy_lo + o));
+            zl[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (r + 8 * u < r1) {
+          float d[8], z[8];
+          unpack8(dh[u], dl[u], has_lo, d);
+          unpack8(zh[u], zl[u], has_lo, z);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a[k] += d[k];
+            b[k] += d[k] * ((z[k] - mu[k]) * rsd[k]);
+          }
+        }
     }
   }
+  const int t = threadIdx.x;
+  const int c = blockIdx.x * 256 + t;
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
 #pragma unroll
@@ -604,88 +680,137 @@ bn_bwd_stage1_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat1
     __syncthreads();
     float s = 0.f;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) s += sm[y][threadIdx.x];
-    const int c = blockIdx.x * 256 + threadIdx.x;
+    for (int y = 0; y < 8; ++y) s += sm[y][t];
     if (c < ld) ws[(static_cast<size_t>(rs) * 2 + which) * ld + c] = s;
     __syncthreads();
   }
-}
-// block = 32 columns x 8 partial lanes, loads batched; fixed summation order
-__global__ void __launch_bounds__(256)
-bn_bwd_stage2_kernel(const float* __restrict__ ws, int ld, int N, float* __restrict__ sums,
-                     float* __restrict__ g_beta) {
-  __shared__ float sm[2][8][32];
-  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float s1 = 0.f, s2 = 0.f;
-  if (c < N) {
-    for (int r = gl; r < COLSUM_RS; r += 32) {  // 4 partial rows x 2 arrays in flight
-      float a[4], b[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int rr = r + 8 * k;
-        a[k] = rr < COLSUM_RS ? ws[(static_cast<size_t>(rr) * 2 + 0) * ld + c] : 0.f;
-        b[k] = rr < COLSUM_RS ? ws[(static_cast<size_t>(rr) * 2 + 1) * ld + c] : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        s1 += a[k];
-        s2 += b[k];
-      }
-    }
-  }
-  sm[0][gl][cl] = s1;
-  sm[1][gl][cl] = s2;
+  __threadfence();
   __syncthreads();
-  if (gl != 0 || c >= N) return;
-  s1 = 0.f;
-  s2 = 0.f;
+  if (t == 0) last = atomicAdd(&counters[blockIdx.x], 1u);
+  __syncthreads();
+  if (last != BN_RS - 1) return;
+  __threadfence();
+  // final sums of this 256-column group: warp w adds partial rows w, w+8, ... (lane = 8 columns, loads batched),
+  // then the eight warp totals are added in fixed order
+  float f1[8], f2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    s1 += sm[0][k][cl];
-    s2 += sm[1][k][cl];
+    f1[k] = 0.f;
+    f2[k] = 0.f;
   }
-  sums[c] = s1;
-  sums[ld + c] = s2;
-  g_beta[c] += s1;
+  if (col < ld) {
+#pragma unroll 5
+    for (int r = w; r < BN_RS; r += 8) {
+      const float4* pa = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(r) * 2 + 0) * ld + col);
+      const float4* pb = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(r) * 2 + 1) * ld + col);
+      const float4 a0 = __ldcg(pa), a1 = __ldcg(pa + 1), b0 = __ldcg(pb), b1 = __ldcg(pb + 1);
+      f1[0] += a0.x; f1[1] += a0.y; f1[2] += a0.z; f1[3] += a0.w; f1[4] += a1.x; f1[5] += a1.y; f1[6] += a1.z; f1[7] += a1.w;
+      f2[0] += b0.x; f2[1] += b0.y; f2[2] += b0.z; f2[3] += b0.w; f2[4] += b1.x; f2[5] += b1.y; f2[6] += b1.z; f2[7] += b1.w;
+    }
+  }
+  float tot[2];
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[w][lane * 8 + k] = which ? f2[k] : f1[k];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][t];
+    tot[which] = s;
+    __syncthreads();
+  }
+  if (c < N) {
+    sums[c] = tot[0];
+    sums[ld + c] = tot[1];
+    g_beta[c] += tot[0];
+  }
+  if (t == 0) counters[blockIdx.x] = 0u;
 }
-__global__ void __launch_bounds__(256)
+
+// dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy * xhat)), in place over dy; same tiling as bn_apply_kernel
+template <bool X3>
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo,
                     const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
                     int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ sums) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
-  if (c >= ld) return;
+  __shared__ float s_mu[8][256], s_rs[8][256], s_m1[8][256], s_m2[8][256];
+  const int cb = blockIdx.x * BN_SPAN;
   const float invB = 1.0f / static_cast<float>(B);
-  float mu[8], rs[8], m1[8], m2[8];
+  const int t = threadIdx.x;
+  const int c = cb + (t << 3);
+  if (c >= ld) return;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const bool ok = c + k < N;
-    mu[k] = ok ? mean[c + k] : 0.f;
-    rs[k] = ok ? rstd[c + k] : 0.f;
-    m1[k] = ok ? sums[c + k] * invB : 0.f;
-    m2[k] = ok ? sums[ld + c + k] * invB : 0.f;
+    s_mu[k][t] = ok ? __ldg(mean + c + k) : 0.f;
+    s_rs[k][t] = ok ? __ldg(rstd + c + k) : 0.f;
+    s_m1[k][t] = ok ? __ldg(sums + c + k) * invB : 0.f;
+    s_m2[k][t] = ok ? __ldg(sums + ld + c + k) * invB : 0.f;
   }
   const int step = static_cast<int>(gridDim.y);
-  for (int r0 = blockIdx.y; r0 < B; r0 += 4 * step) {
-    float ds[4][8], zs[4][8];
+  constexpr int R = X3 ? 2 : 4;  // rows in flight (two arrays each)
+  for (int r0 = blockIdx.y; r0 < B; r0 += R * step) {
+    uint32_t dh[R][4], dl[R][4], zh[R][4], zl[R][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)  // eight independent 16-byte loads in flight
+    for (int u = 0; u < R; ++u)
       if (r0 + u * step < B) {
         const size_t o = static_cast<size_t>(r0 + u * step) * ld + c;
-        load8(dy_hi, dy_lo, o, ds[u]);
-        load8(z_hi, z_lo, o, zs[u]);
+        const uint4 a = *reinterpret_cast<const uint4*>(dy_hi + o);
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+        dh[u][0] = a.x; dh[u][1] = a.y; dh[u][2] = a.z; dh[u][3] = a.w;
+        zh[u][0] = b.x; zh[u][1] = b.y; zh[u][2] = b.z; zh[u][3] = b.w;
+        if (X3) {
+          const uint4 e = *reinterpret_cast<const uint4*>(dy_lo + o);
+          const uint4 f = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+          dl[u][0] = e.x; dl[u][1] = e.y; dl[u][2] = e.z; dl[u][3] = e.w;
+          zl[u][0] = f.x; zl[u][1] = f.y; zl[u][2] = f.z; zl[u][3] = f.w;
+        }
       }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int jj = 0; jj < 2; ++jj) {
+      float mu[4], rs[4], m1[4], m2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mu[i] = s_mu[4 * jj + i][t];
+        rs[i] = s_rs[4 * jj + i][t];
+        m1[i] = s_m1[4 * jj + i][t];
+        m2[i] = s_m2[4 * jj + i][t];
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (r0 + u * step < B) {
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int j = 2 * jj + w;
+            float d[2] = {bf_lo(dh[u][j]), bf_hi(dh[u][j])};
+            float z[2] = {bf_lo(zh[u][j]), bf_hi(zh[u][j])};
+            if (X3) {
+              d[0] += bf_lo(dl[u][j]);
+              d[1] += bf_hi(dl[u][j]);
+              z[0] += bf_lo(zl[u][j]);
+              z[1] += bf_hi(zl[u][j]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = 2 * w + e;
+              const float xh = (z[e] - mu[i]) * rs[i];
+              d[e] = (c + 4 * jj + i < N) ? rs[i] * (d[e] - m1[i] - xh * m2[i]) : 0.f;
+            }
+            split2(d[0], d[1], dh[u][j], dl[u][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
       const int r = r0 + u * step;
-      if (r >= B) break;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xh = (zs[u][k] - mu[k]) * rs[k];
-        ds[u][k] = (c + k < N) ? rs[k] * (ds[u][k] - m1[k] - xh * m2[k]) : 0.f;
+      if (r < B) {
+        const size_t o = static_cast<size_t>(r) * ld + c;
+        *reinterpret_cast<uint4*>(dy_hi + o) = make_uint4(dh[u][0], dh[u][1], dh[u][2], dh[u][3]);
+        if (X3) *reinterpret_cast<uint4*>(dy_lo + o) = make_uint4(dl[u][0], dl[u][1], dl[u][2], dl[u][3]);
       }
-      store8(dy_hi, dy_lo, static_cast<size_t>(r) * ld + c, ds[u]);
     }
   }
 }
@@ -1007,29 +1132,42 @@ int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int
                __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st) {
   if (B <= 0) return 0;
   const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
-  const int gx = ((ld >> 3) + 255) / 256;
-  int gy = 148 * 8 / gx;
-  gy = gy > B ? B : gy;
-  bn_apply_kernel<<<dim3(gx, gy), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr, 1.0f / keep,
-                                                 seed, y_hi, y_lo);
+  const int gx = (ld + BN_SPAN - 1) / BN_SPAN;
+  int gy = 148 * 4 / gx;  // one wave at four blocks per SM
+  gy = gy < 1 ? 1 : (gy > B ? B : gy);
+  if (z_lo)
+    bn_apply_kernel<true><<<dim3(gx, gy), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr, 1.0f / keep,
+                                                         seed, y_hi, y_lo);
+  else
+    bn_apply_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr, 1.0f / keep,
+                                                          seed, y_hi, y_lo);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
-                    float* ws, float* sums, float* g_beta, cudaStream_t st) {
-  dim3 grid((ld + 255) / 256, COLSUM_RS);
-  bn_bwd_stage1_kernel<<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws);
-  bn_bwd_stage2_kernel<<<(N + 31) / 32, 256, 0, st>>>(ws, ld, N, sums, g_beta);
+                    float* ws, unsigned int* counters, float* sums, float* g_beta, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (ld > 256 * 512) return static_cast<int>(cudaErrorInvalidValue);  // 512 counters
+  dim3 grid((ld + 255) / 256, BN_RS);
+  if (dy_lo)
+    bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws, counters,
+                                                     sums, g_beta);
+  else
+    bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws, counters,
+                                                      sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
                    const float* sums, cudaStream_t st) {
   if (B <= 0) return 0;
-  const int gx = ((ld >> 3) + 255) / 256;
-  int gy = 148 * 8 / gx;
-  gy = gy > B ? B : gy;
-  bn_bwd_apply_kernel<<<dim3(gx, gy), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
+  const int gx = (ld + BN_SPAN - 1) / BN_SPAN;
+  int gy = 148 * 4 / gx;
+  gy = gy < 1 ? 1 : (gy > B ? B : gy);
+  if (dy_lo)
+    bn_bwd_apply_kernel<true><<<dim3(gx, gy), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
+  else
+    bn_bwd_apply_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, sums);
   return static_cast<int>(cudaGetLastError());
 }
 

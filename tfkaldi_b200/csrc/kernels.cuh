@@ -83,7 +83,7 @@ int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int
 // backward: sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat; g_beta += sum_B dy.  ws >= 256*ld floats
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
-                    const float* rstd, float* ws, float* sums, float* g_beta, cudaStream_t st);
+                    const float* rstd, float* ws, unsigned int* counters, float* sums, float* g_beta, cudaStream_t st);
 // dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy*xhat)), written in place over dy
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
