@@ -1,0 +1,248 @@
+"""Parity at BASELINE.json's FULL sizes (C2: 440-6x2048-1936, 8192 frames; C4: + batch-norm + dropout 0.5,
+3401 pdf-ids, 4096 frames; C5: one 100 000-frame utterance), through the C-ABI.
+
+The small-size suite (test_gpu_parity.py) compares everything element by element; here the shapes are the
+ones bench.py times, so the kernels take the code paths that only exist at scale (74 CTA pairs with static
+longest-first work lists, half-width tiles, split-K wgrad on layer 0, the fused wgrad+dgrad launch, decoder
+tiling over max_frames).  Two kinds of check:
+  * direct: the oracle still finishes one full-size step in seconds (fp32 GEMMs on the host cores), so loss,
+    gradients and log-likelihoods are compared with it under the same 1e-3 bounds as the small suite;
+  * size-independent properties of the path: ln(O) first loss and exactly-zero hidden gradients from the
+    reference's zero-initialised output layer (classifiers/dnn.py:67-68), micro-batch and frame-order
+    invariance of the accumulated gradients (trainer.py:165-175 sums over frames), posterior rows summing to
+    one, log-likelihood == log(posterior) - log(prior) (nnet.py:280-286), independence of the decoder's
+    output from how a long utterance is tiled, dropout keep-rate and 1/keep scaling (activation.py:140-141).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.dnn_oracle import OracleConfig, OracleDNN, reference_init, set_matmul_backend
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+TOL = 1e-3
+C2 = dict(num_layers=6, input_dim=440, hidden_dim=2048, output_dim=1936)
+C4 = dict(num_layers=6, input_dim=440, hidden_dim=2048, output_dim=3401, batch_norm=True, keep_prob=0.5)
+
+
+@pytest.fixture(autouse=True)
+def fast_oracle_gemms():
+    """full-size fp32 GEMMs through torch-CPU (MKL, every host core) instead of numpy's BLAS"""
+    set_matmul_backend("torch")
+    yield
+    set_matmul_backend("numpy")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+def grad_err(got, want):
+    want = np.asarray(want, np.float64)
+    return np.abs(np.asarray(got, np.float64) - want) / max(np.abs(want).max(), 1e-30)
+
+
+def make(cfg_kw, frames, precision, seed, random_out=True, oracle=True):
+    from tfkaldi_b200.engine import Engine
+
+    cfg = OracleConfig(**cfg_kw)
+    rng = np.random.default_rng(seed)
+    params = reference_init(cfg, rng)
+    if random_out:
+        L = cfg.num_layers
+        params[f"W{L}"] = (rng.standard_normal(params[f"W{L}"].shape) / math.sqrt(cfg.hidden_dim)).astype(np.float32)
+        for l in range(L + 1):
+            params[f"b{l}"] = (0.1 * rng.standard_normal(params[f"b{l}"].shape)).astype(np.float32)
+    eng = Engine(cfg.num_layers, cfg.input_dim, cfg.hidden_dim, cfg.output_dim, frames, nonlin=cfg.nonlin,
+                 batch_norm=cfg.batch_norm, keep_prob=cfg.keep_prob, precision=precision, seed=1000)
+    eng.load_params(params)
+    return (OracleDNN(cfg, params) if oracle else None), eng, rng, cfg, params
+
+
+def check_grads(eng, orc, cfg, min_ok):
+    from tfkaldi_b200 import _lib as L
+
+    kinds = {"W": L.T_GRAD_W, "b": L.T_GRAD_B, "beta": L.T_GRAD_BETA}
+    for k, want in orc.grads.items():
+        stem = k.rstrip("0123456789")
+        layer = int(k[len(stem):])
+        if cfg.batch_norm and stem == "b" and layer < cfg.num_layers:
+            continue  # bias under batch-norm: exactly 0 in exact arithmetic, round-off on both sides
+        e = grad_err(eng.get_tensor(kinds[stem], layer), want)
+        # ReLU boundary flips (module docstring of test_gpu_parity.py): the bound holds for all but a tiny fraction
+        assert (e < TOL).mean() >= min_ok and e.max() < 0.25, (k, float(e.max()), float((e < TOL).mean()))
+
+
+def test_c2_full_size_step_against_oracle(cuda_device):
+    """configs[1] at full size in the fp32-equivalent mode: summed loss, every gradient tensor, the loss the
+    optimizer step returns, then log-likelihoods of 1024 frames decoded from the oracle's updated weights."""
+    from tfkaldi_b200 import _lib as L
+
+    B = 8192
+    orc, eng, rng, cfg, _ = make(C2, B, "bf16x3", seed=42)
+    x = rng.standard_normal((B, 440)).astype(np.float32)
+    y = rng.integers(0, 1936, B)
+    eng.accumulate(x, y)
+    orc.accumulate(x, y)
+    assert abs(eng.get_scalar(L.S_LOSS_SUM) - orc.loss_sum) <= TOL * orc.loss_sum
+    assert eng.get_scalar(L.S_NUM_FRAMES) == B
+    check_grads(eng, orc, cfg, 0.995)
+    lg, lo = eng.apply(1e-3), orc.apply(1e-3)
+    assert abs(lg - lo) <= TOL * max(1.0, abs(lo))
+    eng.load_params(orc.p)
+    prior = (rng.random(1936) + 0.1).astype(np.float32)
+    prior /= prior.sum()
+    ll_g, ll_o = eng.loglik(x[:1024], prior).cpu().numpy(), orc.loglik(x[:1024], prior)
+    assert rel(ll_g, ll_o).max() < TOL
+    top2 = np.sort(ll_o, axis=1)[:, -2:]
+    sure = (top2[:, 1] - top2[:, 0]) > 2 * TOL * np.maximum(1, np.abs(top2[:, 1]))
+    assert sure.mean() > 0.9 and np.array_equal(ll_g.argmax(1)[sure], ll_o.argmax(1)[sure])
+
+
+def test_c4_full_size_step_against_oracle(cuda_device):
+    """configs[3] at full size: batch-norm statistics over 4096 frames, Philox dropout masks (keep 0.5), 3401
+    ragged pdf-ids.  Loss, gradients (beta included), and the moving statistics after one micro-batch."""
+    from tfkaldi_b200 import _lib as L
+
+    B = 4096
+    orc, eng, rng, cfg, _ = make(C4, B, "bf16x3", seed=43)
+    x = rng.standard_normal((B, 440)).astype(np.float32)
+    y = rng.integers(0, 3401, B)
+    eng.set_dropout_seed(4321)
+    eng.accumulate(x, y)
+    orc.accumulate(x, y, dropout_seed=4321)
+    assert abs(eng.get_scalar(L.S_LOSS_SUM) - orc.loss_sum) <= TOL * orc.loss_sum
+    check_grads(eng, orc, cfg, 0.99)
+    for l in range(6):  # EMA of the batch statistics, once per micro-batch (trainer.py:164-168): continuous -> strict
+        assert rel(eng.get_tensor(L.T_BN_MOVING_MEAN, l), orc.p[f"moving_mean{l}"]).max() < TOL, l
+        assert rel(eng.get_tensor(L.T_BN_MOVING_VAR, l), orc.p[f"moving_var{l}"]).max() < TOL, l
+    lg, lo = eng.apply(1e-3), orc.apply(1e-3)
+    assert abs(lg - lo) <= TOL * max(1.0, abs(lo))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_c2_first_step_facts_at_full_size(cuda_device, precision):
+    """Zero-initialised output layer (classifiers/dnn.py:67-68): logits == 0 => loss/frame == ln(1936) whatever the
+    numeric mode, the hidden layers receive an exactly-zero gradient (dX = dZ.W^T = 0) and Adam of an exactly-zero
+    gradient is an exactly-zero update: after the first optimizer step only layer 6 has moved."""
+    from tfkaldi_b200 import _lib as L
+
+    B = 8192
+    _, eng, rng, _, params = make(C2, B, precision, seed=44, random_out=False, oracle=False)
+    x = rng.standard_normal((B, 440)).astype(np.float32)
+    y = rng.integers(0, 1936, B)
+    loss = eng.train_step(x, y, 1e-3)
+    assert abs(loss - math.log(1936)) < 1e-5
+    for l in range(6):
+        assert np.array_equal(eng.get_tensor(L.T_WEIGHTS, l), params[f"W{l}"]), l
+        assert not eng.get_tensor(L.T_BIASES, l).any(), l
+    w6 = eng.get_tensor(L.T_WEIGHTS, 6)
+    # Adam's first step is lr * g/(|g| + eps): every output weight whose gradient is not ~0 moves by ~lr
+    assert np.abs(w6).max() <= 1.001e-3 and (np.abs(w6) > 0.9e-3).mean() > 0.95
+    assert eng.get_scalar(L.S_GLOBAL_STEP) == 1 and eng.get_scalar(L.S_NUM_FRAMES) == 0
+
+
+def test_c2_gradients_do_not_depend_on_batching_or_frame_order(cuda_device):
+    """The accumulated gradient is a SUM over frames (trainer.py:165-169): one 8192-frame call, four ragged
+    micro-batches, and the same frames in another order give the same accumulators up to fp32 summation order —
+    in the timed bf16 mode, where each frame's forward/backward arithmetic is identical in all three runs."""
+    from tfkaldi_b200 import _lib as L
+
+    B = 8192
+    _, a, rng, _, params = make(C2, B, "bf16", seed=45, oracle=False)
+    x = rng.standard_normal((B, 440)).astype(np.float32)
+    y = rng.integers(0, 1936, B)
+    a.accumulate(x, y)
+    ga = [a.get_tensor(L.T_GRAD_W, l) for l in range(7)] + [a.get_tensor(L.T_GRAD_B, l) for l in range(7)]
+    loss_a = a.get_scalar(L.S_LOSS_SUM)
+    a.apply(1e-3)  # re-zeroes the accumulators (trainer.py:350-352) ...
+    a.load_params(params)  # ... and the weights go back to the starting point
+    cuts = [0, 1000, 1001, 5000, B]  # ragged micro-batches, one of a single frame
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        a.accumulate(x[lo:hi], y[lo:hi])
+    assert a.get_scalar(L.S_NUM_FRAMES) == B
+    gb = [a.get_tensor(L.T_GRAD_W, l) for l in range(7)] + [a.get_tensor(L.T_GRAD_B, l) for l in range(7)]
+    loss_b = a.get_scalar(L.S_LOSS_SUM)
+    a.apply(1e-3)
+    a.load_params(params)
+    perm = rng.permutation(B)
+    a.accumulate(x[perm], y[perm])
+    gc = [a.get_tensor(L.T_GRAD_W, l) for l in range(7)] + [a.get_tensor(L.T_GRAD_B, l) for l in range(7)]
+    loss_c = a.get_scalar(L.S_LOSS_SUM)
+    assert abs(loss_a - loss_b) <= 1e-6 * loss_a and abs(loss_a - loss_c) <= 1e-6 * loss_a
+    for i, (u, v, w) in enumerate(zip(ga, gb, gc)):
+        scale = np.abs(u).max()
+        assert scale > 0
+        assert np.abs(u - v).max() <= 1e-4 * scale, ("micro-batches", i)
+        assert np.abs(u - w).max() <= 1e-4 * scale, ("permutation", i)
+
+
+def test_c5_long_utterance_decode(cuda_device):
+    """configs[4]: one 100 000-frame utterance through the decoder entry points.  Frames are independent in
+    eval mode, so (i) the oracle on a random sample of 2048 frames pins the values (1e-3, argmax equal outside
+    the tolerance margin), (ii) every posterior row sums to one, (iii) log-likelihood == log(posterior) -
+    log(prior) (nnet.py:280-286), and (iv) the output must not depend on how the utterance is tiled over the
+    engine's max_frames workspace (16384-frame tiles vs 8192-frame tiles vs decoding the sampled frames alone)."""
+    from tfkaldi_b200.engine import Engine
+
+    T = 100000
+    orc, eng, rng, cfg, params = make(C2, 16384, "bf16x3", seed=46)
+    x = rng.standard_normal((T, 440)).astype(np.float32)
+    prior = (rng.random(1936) + 0.1).astype(np.float32)
+    prior /= prior.sum()
+    ll = eng.loglik(x, prior).cpu().numpy()
+    post = eng.posteriors(x).cpu().numpy()
+    assert ll.shape == (T, 1936) and np.isfinite(ll).all()
+    assert np.abs(post.sum(1, dtype=np.float64) - 1).max() < 1e-4
+    assert np.abs(ll - (np.log(post.astype(np.float64)) - np.log(prior.astype(np.float64)))).max() < 1e-4
+    pick = np.sort(rng.choice(T, 2048, replace=False))
+    want = orc.loglik(x[pick], prior)
+    assert rel(ll[pick], want).max() < TOL
+    top2 = np.sort(want, axis=1)[:, -2:]
+    sure = (top2[:, 1] - top2[:, 0]) > 2 * TOL * np.maximum(1, np.abs(top2[:, 1]))
+    assert sure.mean() > 0.9 and np.array_equal(ll[pick].argmax(1)[sure], want.argmax(1)[sure])
+    alone = eng.loglik(x[pick], prior).cpu().numpy()
+    assert np.abs(alone - ll[pick]).max() <= 5e-5
+    del post
+    eng.close()
+    small = Engine(6, 440, 2048, 1936, 8192, precision="bf16x3", seed=1000)
+    small.load_params(params)
+    ll2 = small.loglik(x, prior).cpu().numpy()
+    assert np.abs(ll2 - ll).max() <= 5e-5
+    moved = np.flatnonzero(ll2.argmax(1) != ll.argmax(1))  # only exact near-ties may change winner
+    if moved.size:
+        top2 = np.sort(ll[moved], axis=1)[:, -2:]
+        assert (top2[:, 1] - top2[:, 0]).max() <= 1e-4
+
+
+def test_dropout_rate_and_scaling_at_full_size(cuda_device):
+    """activation.py:140-141: y = x / keep * floor(keep + u).  On a linear 8192x2048 layer every output is either
+    exactly 0 or the eval-mode output times 1/keep, and the kept fraction of 16.8 M draws is keep +- 5 sigma."""
+    from tfkaldi_b200.engine import Engine
+
+    B, keep = 8192, 0.5
+    cfg = OracleConfig(num_layers=1, input_dim=440, hidden_dim=2048, output_dim=1936, nonlin="linear", keep_prob=keep)
+    rng = np.random.default_rng(47)
+    params = reference_init(cfg, rng)
+    eng = Engine(1, 440, 2048, 1936, B, nonlin="linear", keep_prob=keep, precision="bf16x3", seed=5)
+    eng.load_params(params)
+    x = rng.standard_normal((B, 440)).astype(np.float32)
+    eng.set_dropout_seed(99)
+    dropped = eng.fflayer_fwd(0, x, training=True).cpu().numpy()
+    clean = eng.fflayer_fwd(0, x, training=False).cpu().numpy()
+    kept = dropped != 0
+    n = kept.size
+    assert abs(kept.mean() - keep) < 5 * math.sqrt(keep * (1 - keep) / n) + (clean == 0).mean()
+    assert np.abs(dropped[kept] - clean[kept] / keep).max() <= 1e-4 * np.abs(clean).max()
+    # per-column and per-row keep rates are unbiased too (no striping of the Philox counters over the tile grid)
+    assert np.abs(kept.mean(0) - keep).max() < 6 * math.sqrt(keep * (1 - keep) / B)
+    assert np.abs(kept.mean(1) - keep).max() < 6 * math.sqrt(keep * (1 - keep) / 2048)
+    eng.set_dropout_seed(99)
+    again = eng.fflayer_fwd(0, x, training=True).cpu().numpy()
+    assert np.array_equal(again, dropped)  # same seed, same mask
+    eng.set_dropout_seed(100)
+    other = eng.fflayer_fwd(0, x, training=True).cpu().numpy()
+    assert abs(((other != 0) == kept).mean() - 0.5) < 0.01  # independent masks agree on half of the entries
