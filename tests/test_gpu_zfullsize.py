@@ -62,34 +62,50 @@ def make(cfg_kw, frames, precision, seed, random_out=True, oracle=True):
     return (OracleDNN(cfg, params) if oracle else None), eng, rng, cfg, params
 
 
-def check_grads(eng, orc, cfg, min_ok):
+def check_grads(eng, orc, cfg, tag):
+    """Every gradient tensor against the oracle.  `linear` chains are continuous functions of the arithmetic: strict
+    1e-3 of the tensor's largest magnitude on EVERY element.  ReLU chains are not: of the ~1e8 pre-activations of a
+    full-size batch a few hundred lie within the two implementations' rounding distance (~1e-5) of zero and land on
+    the other side; each such flip changes one frame's back-propagated signal through every layer below it, i.e. ALL
+    elements of the lower layers' dW by ~1/sqrt(frames) of a typical element.  Any two fp32 implementations differ
+    this way (module docstring of test_gpu_parity.py), so ReLU gradients are held to a relative L2 error per tensor
+    instead, and the measured numbers are printed (pytest -rP) for DESIGN.md."""
     from tfkaldi_b200 import _lib as L
 
     kinds = {"W": L.T_GRAD_W, "b": L.T_GRAD_B, "beta": L.T_GRAD_BETA}
+    report = {}
     for k, want in orc.grads.items():
         stem = k.rstrip("0123456789")
         layer = int(k[len(stem):])
         if cfg.batch_norm and stem == "b" and layer < cfg.num_layers:
             continue  # bias under batch-norm: exactly 0 in exact arithmetic, round-off on both sides
-        e = grad_err(eng.get_tensor(kinds[stem], layer), want)
-        # ReLU boundary flips (module docstring of test_gpu_parity.py): the bound holds for all but a tiny fraction
-        assert (e < TOL).mean() >= min_ok and e.max() < 0.25, (k, float(e.max()), float((e < TOL).mean()))
+        got = eng.get_tensor(kinds[stem], layer).astype(np.float64)
+        want = want.astype(np.float64)
+        e = np.abs(got - want) / max(np.abs(want).max(), 1e-30)
+        l2 = float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30))
+        report[k] = (float(e.max()), float((e < TOL).mean()), l2)
+        if cfg.nonlin == "linear":
+            assert e.max() < TOL, (tag, k, report[k])
+        else:
+            assert l2 < 5e-2 and e.max() < 0.25, (tag, k, report[k])
+    print("%s gradient errors {tensor: (max / max|want|, share < 1e-3, relative L2)}: %s" % (tag, report))
 
 
-def test_c2_full_size_step_against_oracle(cuda_device):
+@pytest.mark.parametrize("nonlin", ["linear", "relu"])
+def test_c2_full_size_step_against_oracle(cuda_device, nonlin):
     """configs[1] at full size in the fp32-equivalent mode: summed loss, every gradient tensor, the loss the
     optimizer step returns, then log-likelihoods of 1024 frames decoded from the oracle's updated weights."""
     from tfkaldi_b200 import _lib as L
 
     B = 8192
-    orc, eng, rng, cfg, _ = make(C2, B, "bf16x3", seed=42)
+    orc, eng, rng, cfg, _ = make(dict(C2, nonlin=nonlin), B, "bf16x3", seed=42)
     x = rng.standard_normal((B, 440)).astype(np.float32)
     y = rng.integers(0, 1936, B)
     eng.accumulate(x, y)
     orc.accumulate(x, y)
     assert abs(eng.get_scalar(L.S_LOSS_SUM) - orc.loss_sum) <= TOL * orc.loss_sum
     assert eng.get_scalar(L.S_NUM_FRAMES) == B
-    check_grads(eng, orc, cfg, 0.995)
+    check_grads(eng, orc, cfg, "C2/" + nonlin)
     lg, lo = eng.apply(1e-3), orc.apply(1e-3)
     assert abs(lg - lo) <= TOL * max(1.0, abs(lo))
     eng.load_params(orc.p)
@@ -102,20 +118,22 @@ def test_c2_full_size_step_against_oracle(cuda_device):
     assert sure.mean() > 0.9 and np.array_equal(ll_g.argmax(1)[sure], ll_o.argmax(1)[sure])
 
 
-def test_c4_full_size_step_against_oracle(cuda_device):
-    """configs[3] at full size: batch-norm statistics over 4096 frames, Philox dropout masks (keep 0.5), 3401
-    ragged pdf-ids.  Loss, gradients (beta included), and the moving statistics after one micro-batch."""
+@pytest.mark.parametrize("nonlin", ["linear", "relu"])
+def test_c4_full_size_step_against_oracle(cuda_device, nonlin):
+    """configs[3] at full size: batch-norm statistics over 4096 frames, Philox dropout masks (keep 0.5; the mask is
+    floor(keep + u), independent of the values, so it cannot flip), 3401 ragged pdf-ids.  Loss, gradients (beta
+    included), and the moving statistics after one micro-batch."""
     from tfkaldi_b200 import _lib as L
 
     B = 4096
-    orc, eng, rng, cfg, _ = make(C4, B, "bf16x3", seed=43)
+    orc, eng, rng, cfg, _ = make(dict(C4, nonlin=nonlin), B, "bf16x3", seed=43)
     x = rng.standard_normal((B, 440)).astype(np.float32)
     y = rng.integers(0, 3401, B)
     eng.set_dropout_seed(4321)
     eng.accumulate(x, y)
     orc.accumulate(x, y, dropout_seed=4321)
     assert abs(eng.get_scalar(L.S_LOSS_SUM) - orc.loss_sum) <= TOL * orc.loss_sum
-    check_grads(eng, orc, cfg, 0.99)
+    check_grads(eng, orc, cfg, "C4/" + nonlin)
     for l in range(6):  # EMA of the batch statistics, once per micro-batch (trainer.py:164-168): continuous -> strict
         assert rel(eng.get_tensor(L.T_BN_MOVING_MEAN, l), orc.p[f"moving_mean{l}"]).max() < TOL, l
         assert rel(eng.get_tensor(L.T_BN_MOVING_VAR, l), orc.p[f"moving_var{l}"]).max() < TOL, l
@@ -127,21 +145,28 @@ def test_c4_full_size_step_against_oracle(cuda_device):
 def test_c2_first_step_facts_at_full_size(cuda_device, precision):
     """Zero-initialised output layer (classifiers/dnn.py:67-68): logits == 0 => loss/frame == ln(1936) whatever the
     numeric mode, the hidden layers receive an exactly-zero gradient (dX = dZ.W^T = 0) and Adam of an exactly-zero
-    gradient is an exactly-zero update: after the first optimizer step only layer 6 has moved."""
+    gradient is an exactly-zero update: after the first optimizer step only layer 6 has moved — by the closed form
+    of Adam's first step, -lr_1 * 0.1 g / (sqrt(0.001 g^2) + 1e-8) with g = clip(G / frames) (trainer.py:174-184)."""
     from tfkaldi_b200 import _lib as L
 
     B = 8192
     _, eng, rng, _, params = make(C2, B, precision, seed=44, random_out=False, oracle=False)
     x = rng.standard_normal((B, 440)).astype(np.float32)
     y = rng.integers(0, 1936, B)
-    loss = eng.train_step(x, y, 1e-3)
+    eng.accumulate(x, y)
+    for l in range(6):
+        assert not eng.get_tensor(L.T_GRAD_W, l).any() and not eng.get_tensor(L.T_GRAD_B, l).any(), l
+    g = np.clip(eng.get_tensor(L.T_GRAD_W, 6).astype(np.float64) / B, -1, 1)
+    assert np.abs(g).max() > 0
+    loss = eng.apply(1e-3)
     assert abs(loss - math.log(1936)) < 1e-5
     for l in range(6):
         assert np.array_equal(eng.get_tensor(L.T_WEIGHTS, l), params[f"W{l}"]), l
         assert not eng.get_tensor(L.T_BIASES, l).any(), l
+    lr1 = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    want = -lr1 * 0.1 * g / (np.sqrt(0.001 * g * g) + 1e-8)
     w6 = eng.get_tensor(L.T_WEIGHTS, 6)
-    # Adam's first step is lr * g/(|g| + eps): every output weight whose gradient is not ~0 moves by ~lr
-    assert np.abs(w6).max() <= 1.001e-3 and (np.abs(w6) > 0.9e-3).mean() > 0.95
+    assert np.abs(w6).max() <= 1.001e-3 and np.abs(w6 - want).max() < 2e-6
     assert eng.get_scalar(L.S_GLOBAL_STEP) == 1 and eng.get_scalar(L.S_NUM_FRAMES) == 0
 
 
