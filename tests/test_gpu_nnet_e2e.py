@@ -113,3 +113,55 @@ def test_train_decode_pipeline(cuda_device, tmp_path, batch_norm, dropout, add_l
         pos = int(out.scp_data[i][1])
         assert raw[pos - len(utt):pos] == utt.encode() and raw[pos:pos + 5] == b"\0BFM "
         assert struct.unpack("<bibi", raw[pos + 5:pos + 15]) == (4, got.shape[0], 4, 183)
+
+
+def test_tensorflow_checkpoints_through_the_trainer_and_decoder(cuda_device, tmp_path):
+    """A model saved the way the reference saves it (tf.train.Saver: V1 single file or V2 index + data shard,
+    trainer.py:448-486) restores through Trainer.restore_model / restore_trainer / Decoder.restore exactly like this
+    engine's own .npz: bit-identical parameters, training variables, and posteriors."""
+    from tfkaldi_b200.neuralNetworks import tf_checkpoint
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.decoder import Decoder
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+
+    def make_dnn():
+        return DNN(50, 2, 64, act.Dropout(act.TfActivation(act.Batchnorm(None), act.relu), 0.8), False)
+
+    rng = np.random.default_rng(0)
+    tr = CrossEnthropyTrainer(make_dnn(), 120, 64, 64, 1e-3, 1.0, 1000, 2, precision="bf16x3", seed=3)
+    tr.initialize()
+    x = [rng.standard_normal((t, 120)).astype(np.float32) for t in (40, 64)]
+    y = [rng.integers(0, 50, t).astype(np.uint32) for t in (40, 64)]
+    for _ in range(3):
+        tr.update(x, y)
+    tr.halve_learning_rate()
+    want = tr.engine.dump_params()
+    # (a) V2, written by export_tf_checkpoint; (b) V1, the r0.11 format, from the same arrays
+    tr.export_tf_checkpoint(str(tmp_path / "v2model"))
+    tf_checkpoint.write_v1(str(tmp_path / "v1model"), tr._model_arrays())
+    trainvars = {"train_variables/global_step": np.array(3, np.int32), "train_variables/learning_rate_fact": np.array(0.5, np.float32),
+                 "train_variables/num_frames": np.array(0, np.int32)}  # the reference's saver holds more than we need
+    tf_checkpoint.write_v1(str(tmp_path / "v1model_trainvars"), trainvars)
+    tr.save_model(str(tmp_path / "own"))
+    probe = rng.standard_normal((33, 120)).astype(np.float32)
+    outs = []
+    for name in ("own", "v2model", "v1model"):
+        dec = Decoder(make_dnn(), 120, 64, precision="bf16x3")
+        dec.restore(str(tmp_path / name))
+        got = dec.engine.dump_params()
+        for k, v in want.items():
+            assert np.array_equal(got[k], v), (name, k)
+        outs.append(dec(probe))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    fresh = CrossEnthropyTrainer(make_dnn(), 120, 64, 64, 1e-3, 1.0, 1000, 2, precision="bf16x3", seed=99)
+    fresh.initialize()
+    fresh.restore_trainer(str(tmp_path / "v1model"))
+    assert fresh.global_step == 3
+    from tfkaldi_b200 import _lib as L
+
+    assert fresh.engine.get_scalar(L.S_LR_FACT) == 0.5
+    got = fresh.engine.dump_params()
+    assert all(np.array_equal(got[k], v) for k, v in want.items())
+    with pytest.raises(FileNotFoundError):
+        fresh.restore_model(str(tmp_path / "nothing_here"))

@@ -29,18 +29,16 @@ class Decoder(object):
         return self.engine.loglik(inputs, prior, out=out)
 
     def restore(self, filename):
-        """load the model written by Trainer.save_model (decoder.py:73-81)"""
-        from .trainer import Trainer
+        """load the model written by Trainer.save_model — or by the reference's own saver (decoder.py:73-81)"""
+        from .trainer import MODEL_NAMES, read_model_file
 
-        path = Trainer._path(filename)
-        names = {"parameters/weights": "W", "parameters/biases": "b", "activation/batch_norm/beta": "beta",
-                 "activation/batch_norm/moving_mean": "moving_mean", "activation/batch_norm/moving_variance": "moving_var"}
         params = {}
-        with np.load(path) as arrays:
-            for key in arrays.files:
-                if key == "Classifier/initialisedlayers":
-                    self.engine.set_active_layers(int(arrays[key]) + 1)
-                    continue
-                _, layer, rest = key.split("/", 2)
-                params[names[rest] + layer[len("layer"):]] = arrays[key]
+        for key, val in read_model_file(filename).items():
+            if key == "Classifier/initialisedlayers":
+                self.engine.set_active_layers(int(val) + 1)
+                continue
+            if not key.startswith("Classifier/"):
+                continue
+            _, layer, rest = key.split("/", 2)
+            params[MODEL_NAMES[rest] + layer[len("layer"):]] = val
         self.engine.load_params(params)

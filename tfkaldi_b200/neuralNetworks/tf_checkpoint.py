@@ -444,9 +444,9 @@ def read_v1(path, verify=True):
     return out
 
 
-def _ordered_string(s: bytes) -> bytes:  # OrderedCode::WriteString
-    return s.replace(b"\x00", b"\x00\xff").replace(b"\xff", b"\xff\x00") + b"\x00\x01" if b"\xff" not in s and b"\x00" not in s \
-        else bytes(b for c in s for b in ((0, 0xFF) if c == 0 else (0xFF, 0) if c == 0xFF else (c,))) + b"\x00\x01"
+def _ordered_string(s: bytes) -> bytes:
+    """OrderedCode::WriteString: 0x00 -> 00 ff, 0xff -> ff 00, terminated by 00 01"""
+    return bytes(b for c in s for b in ((0, 0xFF) if c == 0 else (0xFF, 0) if c == 0xFF else (c,))) + b"\x00\x01"
 
 
 def _v1_key(name: str, rank: int) -> bytes:

@@ -26,6 +26,25 @@ from .. import _lib as L
 from ..engine import Engine
 
 
+# reference TF variable name (below Classifier/layer<l>/) -> engine tensor stem
+MODEL_NAMES = {"parameters/weights": "W", "parameters/biases": "b", "activation/batch_norm/beta": "beta",
+               "activation/batch_norm/moving_mean": "moving_mean", "activation/batch_norm/moving_variance": "moving_var"}
+
+
+def read_model_file(filename):
+    """{variable name: array} from `<filename>.npz` (written here) or, when there is none, from the TensorFlow
+    checkpoint the reference's savers leave at `filename` (V1 single file or V2 .index/.data; tf_checkpoint.py)."""
+    path = filename if filename.endswith(".npz") else filename + ".npz"
+    if os.path.exists(path):
+        with np.load(path) as arrays:
+            return {k: arrays[k] for k in arrays.files}
+    from . import tf_checkpoint
+
+    if tf_checkpoint.find(filename) is None:
+        raise FileNotFoundError("neither %s nor a TensorFlow checkpoint at %s" % (path, filename))
+    return tf_checkpoint.read(filename)
+
+
 class _Op(object):
     """stand-in for a tf.Operation: something with .run()"""
 
@@ -322,23 +341,24 @@ class Trainer(object, metaclass=ABCMeta):
         for key, val in self.engine.dump_params().items():
             stem = key.rstrip("0123456789")
             layer = key[len(stem):]
-            name = {"W": "parameters/weights", "b": "parameters/biases", "beta": "activation/batch_norm/beta",
-                    "moving_mean": "activation/batch_norm/moving_mean", "moving_var": "activation/batch_norm/moving_variance"}[stem]
+            name = {v: k for k, v in MODEL_NAMES.items()}[stem]
             out["Classifier/layer%s/%s" % (layer, name)] = val
         if self.control_ops is not None:
             out["Classifier/initialisedlayers"] = np.array(int(self.engine.get_scalar(L.S_ACTIVE_LAYERS)) - 1, np.int32)
         return out
 
     def _load_model_arrays(self, arrays):
-        names = {"parameters/weights": "W", "parameters/biases": "b", "activation/batch_norm/beta": "beta",
-                 "activation/batch_norm/moving_mean": "moving_mean", "activation/batch_norm/moving_variance": "moving_var"}
         params = {}
-        for key in arrays.files:
+        for key in arrays:
             if key == "Classifier/initialisedlayers":
                 self.engine.set_active_layers(int(arrays[key]) + 1)
                 continue
+            if not key.startswith("Classifier/"):
+                continue
             _, layer, rest = key.split("/", 2)
-            params[names[rest] + layer[len("layer"):]] = arrays[key]
+            if rest not in MODEL_NAMES:
+                raise ValueError("checkpoint variable %r is not part of the DNN classifier" % key)
+            params[MODEL_NAMES[rest] + layer[len("layer"):]] = arrays[key]
         self.engine.load_params(params)
 
     @staticmethod
@@ -349,8 +369,15 @@ class Trainer(object, metaclass=ABCMeta):
         np.savez(self._path(filename), **self._model_arrays())
 
     def restore_model(self, filename):
-        with np.load(self._path(filename)) as arrays:
-            self._load_model_arrays(arrays)
+        """this engine's .npz, or a checkpoint written by the reference's tf.train.Saver (V1 or V2 format)"""
+        self._load_model_arrays(read_model_file(filename))
+
+    def export_tf_checkpoint(self, filename):
+        """the model as a TensorFlow V2 checkpoint under the reference's variable names (tf.train.Saver().restore
+        of the reference's graph reads it; trainer.py:456-463)"""
+        from . import tf_checkpoint
+
+        tf_checkpoint.write_v2(filename, self._model_arrays())
 
     def save_trainer(self, filename):
         """model + `train_variables` (global_step, learning_rate_fact) (trainer.py:465-475).  The Adam
@@ -374,9 +401,9 @@ class Trainer(object, metaclass=ABCMeta):
         """model + train_variables.  As in the reference the live Adam moments are left untouched
         (validation rollback keeps them, nnet.py:184-187) unless restore_optimizer=True."""
         self.restore_model(filename)
-        with np.load(self._path(filename + "_trainvars")) as tv:
-            self.engine.set_scalar(L.S_GLOBAL_STEP, int(tv["train_variables/global_step"]))
-            self.engine.set_scalar(L.S_LR_FACT, float(tv["train_variables/learning_rate_fact"]))
+        tv = read_model_file(filename + "_trainvars")
+        self.engine.set_scalar(L.S_GLOBAL_STEP, int(tv["train_variables/global_step"]))
+        self.engine.set_scalar(L.S_LR_FACT, float(tv["train_variables/learning_rate_fact"]))
         if restore_optimizer:
             kinds = {"W": (L.T_ADAM_M_W, L.T_ADAM_V_W), "b": (L.T_ADAM_M_B, L.T_ADAM_V_B), "beta": (L.T_ADAM_M_BETA, L.T_ADAM_V_BETA)}
             with np.load(self._path(filename + "_optimizer")) as slots:
