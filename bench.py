@@ -448,19 +448,103 @@ def run_decode(args):
         "clocks": clocks}))
 
 
+def run_feed(args):
+    """The data plane in front of the hot path: a synthetic Kaldi corpus (feats.ark/scp, per-speaker CMVN archives,
+    gzip'ed pdf alignments) on tmpfs -> AlignmentBatchDispenser -> RawBatchFeeder thread (pinned buffers, copy stream)
+    -> tfk_train_step_raw (device CMVN + splice + the whole C2 step), against the reference's own loop shape
+    (dispenser.get_batch() then trainer.update(), neuralNetworks/nnet.py:157-160) on the same files."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    from tfkaldi_b200 import synth
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+    from tfkaldi_b200.processing import batchdispenser, feature_reader, target_coder
+    from tfkaldi_b200.processing.feeder import RawBatchFeeder
+
+    torch.cuda.set_device(0)
+    c = CONFIGS["c2"]
+    size = 16  # utterances per step x ~512 frames = ~8192 frames
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        info = synth.make_corpus(tmp, num_utts=768, min_len=462, max_len=562, feat_dim=40, num_speakers=24, num_pdfs=c["output_dim"], seed=0)
+
+        def dispenser():
+            reader = feature_reader.FeatureReader(tmp + "/feats_shuffled.scp", tmp + "/cmvn.scp", tmp + "/utt2spk", 5, info["max_length"])
+            return batchdispenser.AlignmentBatchDispenser(reader, target_coder.AlignmentCoder(lambda x, y: x, c["output_dim"]), size, info["alifile"])
+
+        dnn = DNN(c["output_dim"], c["num_layers"], c["hidden_dim"], act.TfActivation(None, act.relu), False)
+        tr = CrossEnthropyTrainer(dnn, c["input_dim"], info["max_length"], info["max_length"], 1e-3, 1.0, 1000000, size,
+                                  precision=args.precision, seed=1234)
+        tr.initialize()
+        steps = min(args.steps, 100)
+        feeder = RawBatchFeeder(dispenser(), size)
+        for _ in range(args.warmup):
+            tr.update_prefetched(feeder)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(0); sampler.start()
+        f0, l0, t0 = feeder.frames_out, tr.engine.kernel_launches(), time.perf_counter()
+        for _ in range(steps):
+            loss = tr.update_prefetched(feeder)  # returns the step's loss: one host sync per step
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        frames, launches = feeder.frames_out - f0, tr.engine.kernel_launches() - l0
+        clocks = sampler.stop()
+        feeder.close()
+        # host pipeline alone (no GPU work): how fast the thread can read + pack
+        feeder = RawBatchFeeder(dispenser(), size)
+        b = feeder.get(); feeder.release(b)
+        th, nh = time.perf_counter(), 0
+        for _ in range(200):
+            b = feeder.get(); nh += b.frames; feeder.release(b)
+        host_rate = nh / (time.perf_counter() - th)
+        feeder.close()
+        # the reference's loop shape on the same files: host CMVN + splice, then the step
+        d = dispenser()
+        for _ in range(2):
+            tr.update(*d.get_batch())
+        torch.cuda.synchronize()
+        ts, ns = time.perf_counter(), 0
+        for _ in range(max(5, steps // 10)):
+            x, y = d.get_batch()
+            ns += sum(m.shape[0] for m in x)
+            tr.update(x, y)
+        torch.cuda.synchronize()
+        sync_rate = ns / (time.perf_counter() - ts)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps({
+        "metric": "training frames/sec from Kaldi archives (ark/scp + CMVN + alignments -> full optimizer step)", "value": frames / dt,
+        "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "C2 net fed from a synthetic Kaldi corpus on tmpfs: 768 utterances of 462..562 x 40-dim frames, 16 utterances (~8192 frames) per step",
+                   "mean_frames_per_step": frames / steps},
+        "e2e": {"value": frames / dt, "unit": "frames/s", "h2d_bytes_per_step": int(frames / steps * (40 * 4 + 4)), "d2h_bytes_per_step": 16,
+                "api": "RawBatchFeeder(AlignmentBatchDispenser) -> CrossEnthropyTrainer.update_prefetched -> loss", "last_loss": loss},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / steps,
+        "host_pipeline_frames_per_s": host_rate,
+        "reference_loop_shape": {"value": sync_rate, "unit": "frames/s", "what": "dispenser.get_batch() (host CMVN + splice) then trainer.update(), same engine"},
+        "clocks": clocks}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c5"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c5", "feed"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.config == "c5":
         run_decode(args)
+    elif args.config == "feed":
+        run_feed(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -157,6 +157,12 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream);
  * gradients are already being accumulated. */
 int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, float lr, float* mean_loss_host,
                    void* stream);
+/* tfk_train_step from RAW frames (== tfk_accumulate_raw + tfk_apply; arguments as tfk_accumulate_raw): what the
+ * prefetching feeder (processing/feeder.py) calls once per batch, so that FeatureReader.get_utt's CMVN + splice
+ * (feature_reader.py:42-60) and Trainer.update's padding (trainer.py:276-307) never run on the host. */
+int tfk_train_step_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                       const int32_t* labels, int R, int feat_dim, int context, float lr, float* mean_loss_host,
+                       void* stream);
 
 /* == `update_valid_loss.run(feed_dict)` (trainer.py:186-195, 428): eval-mode forward (moving-stat BN,
  * no dropout) + CE; batch_loss += loss, num_frames += B. */

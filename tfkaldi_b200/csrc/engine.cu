@@ -1237,16 +1237,9 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
 // (== tfk_accumulate + tfk_apply, same arithmetic): the clip+Adam update of a layer's weights is launched
 // on a side stream as soon as that layer's fused wgrad/dgrad kernel has finished, so the HBM-bound Adam
 // pass overlaps the tensor-bound backward kernels of the layers below instead of following them.
-int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, float lr, float* mean_loss_host,
-                   void* stream) {
-  if (!h || !x || !labels) return fail(h, TFK_EINVAL, "tfk_train_step: null argument");
-  if (h->comm != nullptr || h->pending_accumulates > 0) {  // data parallel / open accumulation: plain sequence
-    TFK_TRY(tfk_accumulate(h, x, labels, B, stream));
-    return tfk_apply(h, lr, mean_loss_host, stream);
-  }
-  TFK_TRY(check_frames(h, B, "tfk_train_step"));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+// the step proper, once layer 0's operand is in place (load_input or load_raw)
+static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, int B, float lr, float* mean_loss_host,
+                             cudaStream_t st) {
   if (!h->adam_stream) {
     TFK_CUDA(h, cudaStreamCreateWithFlags(&h->adam_stream, cudaStreamNonBlocking));
     h->layer_events.resize(h->L + 2);
@@ -1254,9 +1247,6 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
     h->colsum_events.resize(h->L + 1);
     for (auto& e : h->colsum_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  Plan* plan;
-  TFK_TRY(get_plan(h, B, &plan));
-  TFK_TRY(load_input(h, x, B, 0, st));
   TFK_TRY(forward_range(h, *plan, B, true, 0, true, st));
   {
     TimerScope ts(h, st, TFK_TIMER_SOFTMAX_CE, 2);
@@ -1322,6 +1312,41 @@ int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, 
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
   }
   return TFK_OK;
+}
+
+int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, float lr, float* mean_loss_host,
+                   void* stream) {
+  if (!h || !x || !labels) return fail(h, TFK_EINVAL, "tfk_train_step: null argument");
+  if (h->comm != nullptr || h->pending_accumulates > 0) {  // data parallel / open accumulation: plain sequence
+    TFK_TRY(tfk_accumulate(h, x, labels, B, stream));
+    return tfk_apply(h, lr, mean_loss_host, stream);
+  }
+  TFK_TRY(check_frames(h, B, "tfk_train_step"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, B, &plan));
+  TFK_TRY(load_input(h, x, B, 0, st));
+  return train_step_loaded(h, plan, labels, B, lr, mean_loss_host, st);
+}
+
+// tfk_train_step fed by the device-side CMVN + splice feeder (== tfk_accumulate_raw + tfk_apply)
+int tfk_train_step_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                       const int32_t* labels, int R, int feat_dim, int context, float lr, float* mean_loss_host,
+                       void* stream) {
+  if (!h || !raw || !utt_offsets || !cmvn || !labels) return fail(h, TFK_EINVAL, "tfk_train_step_raw: null argument");
+  if (h->comm != nullptr || h->pending_accumulates > 0) {
+    TFK_TRY(tfk_accumulate_raw(h, raw, utt_offsets, num_utts, cmvn, labels, R, feat_dim, context, stream));
+    return tfk_apply(h, lr, mean_loss_host, stream);
+  }
+  TFK_TRY(check_frames(h, R, "tfk_train_step_raw"));
+  TFK_TRY(check_raw(h, "tfk_train_step_raw", feat_dim, context, num_utts));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  Plan* plan;
+  TFK_TRY(get_plan(h, R, &plan));
+  TFK_TRY(load_raw(h, raw, utt_offsets, num_utts, cmvn, feat_dim, context, 0, R, st));
+  return train_step_loaded(h, plan, labels, R, lr, mean_loss_host, st);
 }
 
 int tfk_eval_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, void* stream) {

@@ -170,6 +170,16 @@ class Engine:
                                             C.byref(out) if want_loss else None, self._stream()))
         return out.value if want_loss else None
 
+    def train_step_raw(self, raw, utt_offsets, cmvn, labels, feat_dim, context, lr, want_loss=True):
+        """train_step fed by the device-side CMVN + splice feeder (tfk_train_step_raw); arguments as accumulate_raw"""
+        raw, cmvn = self._dev_f32(raw), self._dev_f32(cmvn)
+        utt_offsets, labels = self._dev_i32(utt_offsets), self._dev_i32(labels)
+        out = C.c_float()
+        self._check(self.lib.tfk_train_step_raw(self.h, _ptr(raw), _ptr(utt_offsets), utt_offsets.shape[0] - 1, _ptr(cmvn),
+                                                _ptr(labels), raw.shape[0], int(feat_dim), int(context), float(lr),
+                                                C.byref(out) if want_loss else None, self._stream()))
+        return out.value if want_loss else None
+
     def eval_accumulate(self, x, labels):
         x, labels = self._dev_f32(x), self._dev_i32(labels)
         self._check(self.lib.tfk_eval_accumulate(self.h, _ptr(x), _ptr(labels), x.shape[0], self._stream()))

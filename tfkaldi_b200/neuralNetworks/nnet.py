@@ -69,9 +69,13 @@ class Nnet(object):
             validation_step = step
             trainer.save_trainer(conf["savedir"] + "/training/validated")
             num_retries = 0
+        prefetching = hasattr(dispenser, "get_on_device")  # a processing.feeder.RawBatchFeeder around the dispenser
         while step < num_steps:
-            batch_data, batch_labels = dispenser.get_batch()
-            loss = trainer.update(batch_data, batch_labels)
+            if prefetching:
+                loss = trainer.update_prefetched(dispenser)
+            else:
+                batch_data, batch_labels = dispenser.get_batch()
+                loss = trainer.update(batch_data, batch_labels)
             print("step %d/%d loss: %f" % (step, num_steps, loss))
             step += 1
             if step % int(conf["valid_frequency"]) == 0 and val_data is not None:
@@ -110,6 +114,8 @@ class Nnet(object):
                 trainer.save_trainer(conf["savedir"] + "/training/step" + str(step))
         trainer.save_model(conf["savedir"] + "/final")
         self.trainer = trainer
+        if prefetching:
+            dispenser.close()  # stops the thread and un-reads what it had prefetched
         # state prior (nnet.py:241-244)
         prior = dispenser.compute_target_count().astype(np.float32)
         prior = prior / prior.sum()

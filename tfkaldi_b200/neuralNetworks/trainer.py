@@ -24,6 +24,7 @@ import torch
 
 from .. import _lib as L
 from ..engine import Engine
+from ..processing.feeder import cmvn_coefficients
 
 
 # reference TF variable name (below Classifier/layer<l>/) -> engine tensor stem
@@ -298,13 +299,26 @@ class Trainer(object, metaclass=ABCMeta):
             if min(lens) < 2 * context_width + 1:
                 raise ValueError("utterance too short to splice")
             offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-            cmvn = np.empty((len(mats), 2, mats[0].shape[1]), np.float32)
-            for i, st in enumerate(stats):  # apply_cmvn's formulas (feature_reader.py:109-115)
-                mean = st[0, :-1] / st[0, -1]
-                cmvn[i, 0] = mean
-                cmvn[i, 1] = 1.0 / np.sqrt(st[1, :-1] / st[0, -1] - np.square(mean))
+            cmvn = np.stack([cmvn_coefficients(st) for st in stats])  # apply_cmvn's formulas (feature_reader.py:109-115)
             labels = np.concatenate(tgts).astype(np.int32)
             self.engine.accumulate_raw(np.concatenate(mats, axis=0), offsets, cmvn, labels, mats[0].shape[1], context_width)
+        return self._apply()
+
+    def update_prefetched(self, feeder):
+        """update() on the next batch of a RawBatchFeeder (processing/feeder.py): the batch was read and packed by the
+        feeder's thread and its host->device copy queued while the previous step was computing; CMVN, splice and the
+        whole step run on the device (tfk_train_step_raw, or accumulate_raw x k + apply for k micro-batches)."""
+        batch = feeder.get_on_device()
+        lr, context = self.learning_rate_cached(), feeder.context_width
+        parts = list(batch.microbatches())
+        if len(parts) == 1:
+            raw, labels, offsets, cmvn = parts[0]
+            loss = self.engine.train_step_raw(raw, offsets, cmvn, labels, batch.feat_dim, context, lr, True)
+            feeder.consumed(batch)
+            return self._log(loss)
+        for raw, labels, offsets, cmvn in parts:
+            self.engine.accumulate_raw(raw, offsets, cmvn, labels, batch.feat_dim, context)
+        feeder.consumed(batch)
         return self._apply()
 
     def _apply(self, want_loss=True):

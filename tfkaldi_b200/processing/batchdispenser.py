@@ -16,9 +16,22 @@ class BatchDispenser(object, metaclass=ABCMeta):
     def __init__(self, feature_reader, target_coder, size, target_path):
         self.feature_reader = feature_reader
         self.target_dict = self.read_target_file(target_path)
-        self.max_target_length = max(target_coder.encode(targets).size for targets in self.target_dict.values())
         self.size = size
         self.target_coder = target_coder
+        # The reference encodes every target string here (for max_target_length, batchdispenser.py:45-49), again for
+        # every batch (:81) and again for the prior (:139).  Parsing a 500-label string costs more than reading the
+        # utterance's features, so the vectors of the first pass are kept: 4 bytes per frame, read-only.
+        self._encoded = {}
+        self.max_target_length = max(self._targets(utt_id).size for utt_id in self.target_dict)
+
+    def _targets(self, utt_id):
+        """encoded (uint32, read-only) target vector of an utterance, parsed once"""
+        enc = self._encoded.get(utt_id)
+        if enc is None:
+            enc = self.target_coder.encode(self.target_dict[utt_id])
+            enc.flags.writeable = False
+            self._encoded[utt_id] = enc
+        return enc
 
     def get_batch(self):
         """(list of [T_u, I] float32, list of uint32 [T_u]); utterances without targets or too short to
@@ -29,7 +42,7 @@ class BatchDispenser(object, metaclass=ABCMeta):
             has_targets = utt_id in self.target_dict
             if has_targets and utt_mat is not None:
                 batch_inputs.append(utt_mat)
-                batch_targets.append(self.target_coder.encode(self.target_dict[utt_id]))
+                batch_targets.append(self._targets(utt_id))
                 continue
             if not has_targets:
                 print("WARNING no targets for %s" % utt_id)
@@ -51,7 +64,7 @@ class BatchDispenser(object, metaclass=ABCMeta):
             if has_targets and long_enough:
                 mats.append(utt_mat)
                 stats.append(reader._cmvn_stats(reader.utt2spk[utt_id]))
-                batch_targets.append(self.target_coder.encode(self.target_dict[utt_id]))
+                batch_targets.append(self._targets(utt_id))
                 continue
             if not has_targets:
                 print("WARNING no targets for %s" % utt_id)
@@ -77,7 +90,7 @@ class BatchDispenser(object, metaclass=ABCMeta):
 
     def compute_target_count(self):
         """occurrences of every label over ALL targets (batchdispenser.py:128-145)"""
-        stacked = np.concatenate([self.target_coder.encode(t) for t in self.target_dict.values()])
+        stacked = np.concatenate([self._targets(utt_id) for utt_id in self.target_dict])
         return np.bincount(stacked, minlength=self.target_coder.num_labels)
 
     @property
