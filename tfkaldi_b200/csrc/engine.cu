@@ -92,9 +92,8 @@ struct Layer {
   float* db_part = nullptr;  // [maxB/32 + 8, ldn] bias-gradient partials written by the dgrad epilogue above
 };
 
-struct Plan {  // TMA descriptors (+ CTA-pair work lists) for one (frames, active layers) shape
+struct Plan {  // TMA descriptors for one (frames, active layers) shape; the work lists they point at live in list_cache
   std::vector<GemmParams> fwd_train, fwd_eval, bwd;
-  std::vector<int*> lists;  // device work lists owned by the plan
 };
 
 }  // namespace
@@ -136,6 +135,8 @@ struct tfk_handle {
   float* tmp_f32 = nullptr;
   int* sched = nullptr;
   std::map<long long, Plan> plans;
+  struct TileLists { int* d; int pairs, stride; };
+  std::map<std::vector<int>, TileLists> list_cache;  // CTA-pair work lists per launch shape (finish_params)
   // trainer scalars
   long long global_step = 0;
   double lr_fact = 1.0;
@@ -251,20 +252,40 @@ int drain_timers(tfk_handle* h) {
 // ------------------------------------------------------------------ plans
 void base_operands(tfk_handle* h, GemmSpec& s) { s.nsplit = h->x3 ? 3 : 1; }
 
+// Tensor maps are rebuilt for every new frame count (host-only, microseconds).  The per-pair work lists are not:
+// computing them (longest-first assignment + the half-tile search) costs ~2 ms per launch shape and uploading them a
+// cudaMalloc + synchronous copy, which with utterance batches of a different length every step (the reference's
+// normal case, trainer.py:276-307) was 40 ms per step against a 1.2 ms step.  The lists depend on the frame count
+// only through the tile / k-block counts, so they are cached per launch SHAPE and owned by the handle.
 int finish_params(tfk_handle* h, Plan& plan, const GemmSpec* s, int n, GemmParams* gp, const char* what, int l) {
+  (void)plan;
   char err[256] = {0};
   if (gemm_build_params(s, n, h->sched, gp, err, sizeof(err), h->two_cta ? 1 : 0))
     return fail(h, TFK_ECUDA, "%s plan layer %d: %s", what, l, err);
+  std::vector<int> key;
+  if (gp->two_cta) {  // everything gemm_upload_tile_lists reads
+    key = {gp->total_tiles, gp->nprob};
+    for (int i = 0; i < gp->nprob; ++i) {
+      const GemmProblem& p = gp->p[i];
+      const int f[7] = {p.tile_begin, p.tiles_m, p.tiles_n, p.kb_per_split, p.num_kb, p.nsplit, p.N};
+      key.insert(key.end(), f, f + 7);
+    }
+    auto it = h->list_cache.find(key);
+    if (it != h->list_cache.end()) {
+      gp->num_pairs = it->second.pairs;
+      gp->list_stride = it->second.stride;
+      gp->tile_list = it->second.d;
+      return TFK_OK;
+    }
+  }
   int* d = nullptr;
   if (gemm_upload_tile_lists(gp, h->num_sms, &d, err, sizeof(err)))
     return fail(h, TFK_ECUDA, "%s plan layer %d: %s", what, l, err);
-  if (d) plan.lists.push_back(d);
+  if (d) h->list_cache[key] = {d, gp->num_pairs, gp->list_stride};
   return TFK_OK;
 }
 
 void free_plan(Plan& plan) {
-  for (int* d : plan.lists) cudaFree(d);
-  plan.lists.clear();
   for (auto& gp : plan.bwd)
     for (int i = 0; i < 2; ++i)
       if (gp.p[i].peer_tm) {
@@ -392,7 +413,7 @@ int get_plan(tfk_handle* h, int B, Plan** out) {
   const long long key = static_cast<long long>(B) * 64 + h->active;
   auto it = h->plans.find(key);
   if (it == h->plans.end()) {
-    if (h->plans.size() > 64) {
+    if (h->plans.size() > 512) {  // tensor maps only: ~40 KB of host memory each
       cudaDeviceSynchronize();
       for (auto& kv : h->plans) free_plan(kv.second);
       h->plans.clear();
@@ -729,6 +750,7 @@ int tfk_destroy(tfk_handle* h) {
   for (auto e : h->layer_events) cudaEventDestroy(e);
   for (auto e : h->colsum_events) cudaEventDestroy(e);
   for (auto& kv : h->plans) free_plan(kv.second);
+  for (auto& kv : h->list_cache) cudaFree(kv.second.d);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->allocs) cudaFree(p);
   if (h->acc_host) cudaFreeHost(h->acc_host);
@@ -1057,12 +1079,7 @@ int tfk_fflayer_bwd(tfk_handle* h, int layer, const float* dy, float* dx, int B,
     free_plan(scratch);
     return rc;
   }
-  const int brc = backward_layer(h, *plan, B, layer, st, &gp);
-  if (!scratch.lists.empty()) {  // the ad-hoc work list must outlive the launch
-    cudaStreamSynchronize(st);
-    free_plan(scratch);
-  }
-  TFK_TRY(brc);
+  TFK_TRY(backward_layer(h, *plan, B, layer, st, &gp));  // (the work list it uses is owned by h->list_cache)
   if (dx) {
     TimerScope ts(h, st, TFK_TIMER_CONVERT);
     TFK_LAUNCH(h, k_merge_bf16(h->dA_hi[dst], h->dA_lo[dst], ly.ldk, dx, ly.K, B, ly.K, st));
