@@ -70,7 +70,9 @@ def test_batches_match_the_synchronous_path(corpus, size, n):
 
 
 def same_ids(a, b):
-    return a.feature_reader.reader.scp_position == b.feature_reader.reader.scp_position
+    """same place in the scp: un-reading across the end of the list may leave the cursor at 0 instead of len"""
+    ra, rb = a.feature_reader.reader, b.feature_reader.reader
+    return ra.scp_position % len(ra.utt_ids) == rb.scp_position % len(rb.utt_ids)
 
 
 def test_cursor_moves_survive_read_ahead(corpus):
@@ -114,3 +116,94 @@ def test_errors_of_the_thread_reach_the_training_thread(corpus):
     assert "exceeds the feeder capacity" in str(ei.value.__cause__)
     with pytest.raises(ValueError, match="multiple of numutterances_per_minibatch"):
         RawBatchFeeder(d, utts_per_microbatch=3)
+
+
+NNET_CONF = """
+[directories]
+expdir = %s
+[nnet]
+name = dnn
+context_width = 5
+num_hidden_units = 32
+num_hidden_layers = 2
+add_layer_period = 0
+starting_step = 0
+nonlin = relu
+l2_norm = False
+dropout = 1
+batch_norm = False
+num_epochs = 2
+initial_learning_rate = 0.001
+learning_rate_decay = 1
+batch_size = 4
+numutterances_per_minibatch = 2
+valid_batches = 1
+valid_frequency = 2
+valid_adapt = True
+valid_retries = 3
+check_freq = 100
+visualise = False
+"""
+
+
+class RecordingTrainer(object):
+    """stands in for CrossEnthropyTrainer: records WHICH data every update consumed (frames, label checksum)"""
+    log, losses = None, None
+
+    def __init__(self, *a, **kw):
+        self.control_ops = None
+
+    def initialize(self):
+        pass
+
+    def update(self, inputs, targets):  # the reference's loop shape: spliced host batch
+        self.log.append(("update", sum(m.shape[0] for m in inputs), int(sum(int(t.sum()) for t in targets))))
+        return 1.0
+
+    def update_prefetched(self, feeder):  # host half of Trainer.update_prefetched (no device copy here)
+        batch = feeder.get()
+        assert len(list(batch.microbatches())) == 2
+        self.log.append(("update", batch.frames, int(batch.labels.numpy().sum())))
+        feeder.release(batch)
+        return 1.0
+
+    def evaluate(self, inputs, targets):
+        self.log.append(("evaluate", sum(m.shape[0] for m in inputs)))
+        return self.losses.pop(0)
+
+    def halve_learning_rate(self):
+        self.log.append("halve")
+
+    def save_trainer(self, f):
+        self.log.append("save:" + f.rsplit("/", 1)[1])
+
+    def restore_trainer(self, f):
+        self.log.append("restore:" + f.rsplit("/", 1)[1])
+
+    save_model = save_trainer
+
+
+@pytest.mark.parametrize("losses", [[5, 4, 3, 2, 1, 0.5, 0.4, 0.3, 0.2, 0.1], [5, 4, 6, 3.5, 7, 8, 3, 2, 1, 0.5, 0.4, 0.3, 0.2]])
+def test_nnet_train_consumes_the_same_data_with_and_without_prefetching(corpus, tmp_path, monkeypatch, losses):
+    """Nnet.train(dispenser) wraps the dispenser in the feeder by default; with validation rollbacks in the middle of
+    the read-ahead (nnet.py:177-186) every update must still see exactly the batch the synchronous loop sees, and
+    the dispenser must end at the same place."""
+    import configparser
+
+    import tfkaldi_b200.neuralNetworks.nnet as nnet_mod
+
+    monkeypatch.setattr(nnet_mod, "CrossEnthropyTrainer", RecordingTrainer)
+    logs, ends = [], []
+    for prefetch in (False, True):
+        conf = configparser.ConfigParser()
+        conf.read_string(NNET_CONF % str(tmp_path / ("p%d" % prefetch)))
+        RecordingTrainer.log, RecordingTrainer.losses = [], list(losses)
+        d = dispenser(corpus, 4)
+        nnet_mod.Nnet(conf, 13, 50).train(d, prefetch=prefetch)
+        logs.append(RecordingTrainer.log)
+        r = d.feature_reader.reader
+        ends.append(r.scp_position % len(r.utt_ids))
+    assert logs[0] == logs[1] and ends[0] == ends[1]
+    assert sum(1 for e in logs[0] if e[0] == "update") >= 14  # 2 epochs x 7 batches (+ the repeated ones)
+    if 6 in losses:
+        assert "halve" in logs[0]

@@ -37,9 +37,23 @@ class Nnet(object):
         self.dnn = DNN(num_labels, int(self.conf["num_hidden_layers"]), int(self.conf["num_hidden_units"]), activation,
                        int(self.conf["add_layer_period"]) > 0)
 
-    def train(self, dispenser):
-        """train on the dispenser's data (nnet.py:80-244)"""
+    def train(self, dispenser, prefetch=True):
+        """train on the dispenser's data (nnet.py:80-244).
+
+        prefetch=True (default): the dispenser is wrapped in a processing.feeder.RawBatchFeeder — a background thread
+        reads and packs the RAW utterances of the next batches into pinned memory, CMVN + splicing run on the device
+        (same utterances, same order, same cursor semantics for rollback/resume; values equal to the host pipeline to
+        fp32 round-off).  prefetch=False keeps the reference's loop shape: get_batch() (host CMVN + splice) then
+        update(), one after the other."""
         conf = self.conf
+        if conf["numutterances_per_minibatch"] == "-1":
+            numutterances_per_minibatch = dispenser.size
+        else:
+            numutterances_per_minibatch = int(conf["numutterances_per_minibatch"])
+        if prefetch and hasattr(dispenser, "get_raw_batch") and not hasattr(dispenser, "get_on_device"):
+            from ..processing.feeder import RawBatchFeeder
+
+            dispenser = RawBatchFeeder(dispenser, numutterances_per_minibatch, device=self.device)
         val_data, val_labels = zip(*[dispenser.get_batch() for _ in range(int(conf["valid_batches"]))]) if int(conf["valid_batches"]) > 0 else ((), ())
         val_data = list(itertools.chain.from_iterable(val_data)) or None
         val_labels = list(itertools.chain.from_iterable(val_labels)) or None
@@ -48,10 +62,6 @@ class Nnet(object):
         step = int(conf["starting_step"]) - int(conf["starting_step"]) % int(conf["check_freq"])
         for _ in range(step):
             dispenser.skip_batch()
-        if conf["numutterances_per_minibatch"] == "-1":
-            numutterances_per_minibatch = dispenser.size
-        else:
-            numutterances_per_minibatch = int(conf["numutterances_per_minibatch"])
         trainer = CrossEnthropyTrainer(
             self.dnn, self.input_dim, dispenser.max_input_length, dispenser.max_target_length,
             float(conf["initial_learning_rate"]), float(conf["learning_rate_decay"]), num_steps,

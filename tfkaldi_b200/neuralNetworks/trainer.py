@@ -308,7 +308,7 @@ class Trainer(object, metaclass=ABCMeta):
         """update() on the next batch of a RawBatchFeeder (processing/feeder.py): the batch was read and packed by the
         feeder's thread and its host->device copy queued while the previous step was computing; CMVN, splice and the
         whole step run on the device (tfk_train_step_raw, or accumulate_raw x k + apply for k micro-batches)."""
-        batch = feeder.get_on_device()
+        batch = feeder.get_on_device(self.engine.device)
         lr, context = self.learning_rate_cached(), feeder.context_width
         parts = list(batch.microbatches())
         if len(parts) == 1:

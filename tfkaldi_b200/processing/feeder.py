@@ -221,7 +221,8 @@ class RawBatchFeeder(object):
     # ------------------------------------------------------------------ device side
     def _device_buffers(self):
         if self._dev is None:
-            dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+            dev = self.device if self.device is not None else torch.cuda.current_device()
+            dev = torch.device("cuda", dev) if isinstance(dev, int) else torch.device(dev)
             mbs = self.size // self.n
             self._dev = {
                 "device": dev,
@@ -254,9 +255,11 @@ class RawBatchFeeder(object):
         batch.on_device = (raw[:batch.frames], lab[:batch.frames], off, cmvn)
         return batch
 
-    def get_on_device(self):
+    def get_on_device(self, device=None):
         """the next batch with its device views; the compute stream is made to wait for the copy.  If the batch after
         it is already packed, its copy is queued right away so that it overlaps the step about to run."""
+        if device is not None and self._dev is None:
+            self.device = device
         batch = self._staged if self._staged is not None else self._stage(self.get())
         self._staged = None
         self.frames_out += batch.frames
