@@ -960,9 +960,9 @@ int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* err, int errlen) {
-  *d_list = nullptr;
-  if (!params->two_cta) return 0;
+// Host-only half of gemm_upload_tile_lists: the per-pair work lists as a flat [pairs, stride] array (-1 padded).
+void gemm_schedule_tile_lists(const GemmParams* params, int num_sms, std::vector<int>* flat_out, int* pairs_out,
+                              int* stride_out) {
   const int total = params->total_tiles;
   int pairs = num_sms / 2;
   if (pairs > 2 * total) pairs = 2 * total;
@@ -1006,17 +1006,21 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
   // longest-processing-time-first assignment of `items`; returns the makespan
   auto lpt = [&](std::vector<Item> items, std::vector<std::vector<int>>* lists) -> long long {
     std::stable_sort(items.begin(), items.end(), by_cost);
-    std::vector<long long> load(pairs, 0);
     if (lists) lists->assign(pairs, std::vector<int>());
-    for (const auto& it : items) {
-      int best = 0;
-      for (int p = 1; p < pairs; ++p)
-        if (load[p] < load[best]) best = p;
-      if (lists) (*lists)[best].push_back(it.entry);
-      load[best] += it.cost;
-    }
+    // every item goes to the least loaded pair, the lowest-numbered one among equals: a min-heap on (load, pair)
+    typedef std::pair<long long, int> Slot;
+    std::vector<Slot> heap(pairs);
+    for (int p = 0; p < pairs; ++p) heap[p] = Slot(0, p);  // ascending (load, pair): already a valid min-heap
+    auto later = [](const Slot& a, const Slot& b) { return a > b; };
     long long mk = 0;
-    for (long long l : load) mk = l > mk ? l : mk;
+    for (const auto& it : items) {
+      std::pop_heap(heap.begin(), heap.end(), later);
+      Slot& best = heap.back();
+      if (lists) (*lists)[best.second].push_back(it.entry);
+      best.first += it.cost;
+      mk = best.first > mk ? best.first : mk;
+      std::push_heap(heap.begin(), heap.end(), later);
+    }
     return mk;
   };
   auto with_split = [&](int nsplit_tiles) {  // the `nsplit_tiles` cheapest whole tiles become two halves each
@@ -1071,6 +1075,17 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
   std::vector<int> flat(static_cast<size_t>(pairs) * stride, -1);
   for (int p = 0; p < pairs; ++p)
     for (size_t i = 0; i < lists[p].size(); ++i) flat[p * stride + i] = lists[p][i];
+  *pairs_out = pairs;
+  *stride_out = static_cast<int>(stride);
+  flat_out->swap(flat);
+}
+
+int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* err, int errlen) {
+  *d_list = nullptr;
+  if (!params->two_cta) return 0;
+  std::vector<int> flat;
+  int pairs = 0, stride = 0;
+  gemm_schedule_tile_lists(params, num_sms, &flat, &pairs, &stride);
   int* d = nullptr;
   cudaError_t e = cudaMalloc(&d, flat.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(d, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice);
@@ -1080,7 +1095,7 @@ int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* 
     return -2;
   }
   params->num_pairs = pairs;
-  params->list_stride = static_cast<int>(stride);
+  params->list_stride = stride;
   params->tile_list = d;
   *d_list = d;
   return 0;

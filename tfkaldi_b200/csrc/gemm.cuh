@@ -9,6 +9,7 @@
 //   dgrad    dX[B,K]  = dZ[B,N] . W[K,N]^T   A = dZ (K-major)   B = W  (K-major, W row = output col)
 //   wgrad    dW[K,N] += X[B,K]^T . dZ[B,N]   A = X  (MN-major)  B = dZ (MN-major), TMA reduce-add
 #pragma once
+#include <vector>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -131,6 +132,8 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
 // CTA-pair plans only: compute the per-pair longest-processing-time-first work lists and upload them
 // (cudaMalloc; the caller owns *d_list and frees it with cudaFree).
 int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* err, int errlen);
+// the host-only half of it: flat [pairs, stride] lists, -1 padded (deterministic; cached per launch shape by the engine)
+void gemm_schedule_tile_lists(const GemmParams* params, int num_sms, std::vector<int>* flat, int* pairs, int* stride);
 // Launch on `stream`.  `num_sms` = multiprocessor count of the current device.
 int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream);
 // One-time (per process) kernel attribute setup; returns cudaError_t as int.
