@@ -95,3 +95,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert not pat.search(text), os.path.join(base, f)
+
+
+def test_work_list_scheduler_covers_every_tile_exactly_once():
+    """host half of the CTA-pair GEMM (gemm_schedule_tile_lists): `selftest_gemm sched` sweeps 2352 launch shapes
+    (forward, fused wgrad+dgrad, split-K wgrad; ragged N; bf16 / bf16x3) and checks coverage, termination and determinism
+    of the per-pair work lists — no GPU involved."""
+    import subprocess
+
+    binary = os.path.join(ROOT, "tfkaldi_b200", "csrc", "build", "selftest_gemm")
+    if not os.path.exists(binary):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    out = subprocess.run([binary, "sched"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALL PASS" in out.stdout and "2352 launch shapes" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -350,8 +350,75 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   free_mat(A); free_mat(B); cudaFree(D); cudaFree(Dl); cudaFree(bias);
 }
 
+// "sched": the CTA-pair work-list scheduler alone (host code, runs without a GPU).  For a sweep of launch shapes
+// (forward, fused wgrad+dgrad, split-K layer-0 wgrad; ragged N; bf16 and bf16x3) every output tile must be covered
+// exactly once - whole, as its two 128-column halves, or (right half outside N) as its left half only - the lists must
+// be -1 terminated within their stride, no pair may be idle while another holds two items more than it needs to, and
+// the result must be deterministic.
+static int sched_selftest() {
+  constexpr int kHalfShift = 28;  // entry = tile | half << 28 (gemm.cu)
+  int shapes = 0, bad = 0;
+  const int Ns[] = {2048, 1936, 3401, 183, 256, 200};
+  for (int B = 1; B <= 20000; B = B < 600 ? B + 37 : B + 611)
+    for (int N : Ns)
+      for (int kind = 0; kind < 4; ++kind)
+        for (int nsplit = 1; nsplit <= 3; nsplit += 2) {
+          const int H = N > 1000 ? 2048 : 256;
+          GemmParams gp;
+          memset(&gp, 0, sizeof(gp));
+          gp.two_cta = 1;
+          int begin = 0;
+          auto add = [&](int M, int Nn, int K, int ks) {
+            GemmProblem& p = gp.p[gp.nprob++];
+            p.M = M; p.N = Nn; p.K = K; p.nsplit = nsplit;
+            p.tiles_m = (M + 255) / 256; p.tiles_n = (Nn + BN - 1) / BN; p.tile_begin = begin;
+            p.num_kb = (K + BK - 1) / BK; p.ksplit = ks; p.kb_per_split = (p.num_kb + ks - 1) / ks;
+            begin += p.tiles_m * p.tiles_n * ks;
+          };
+          if (kind == 0) add(B, N, H, 1);
+          else if (kind == 1) { add(H, N, B, 1); add(B, H, N, 1); }
+          else if (kind == 2) { const int kb = (B + BK - 1) / BK; add(440, N, B, std::max(1, std::min(9, kb / 16))); }
+          else add(B, N, 440, 1);
+          gp.total_tiles = begin;
+          std::vector<int> flat, again;
+          int pairs = 0, stride = 0, p2 = 0, s2 = 0;
+          gemm_schedule_tile_lists(&gp, 148, &flat, &pairs, &stride);
+          gemm_schedule_tile_lists(&gp, 148, &again, &p2, &s2);
+          ++shapes;
+          bool ok = flat == again && pairs == p2 && stride == s2 && pairs >= 1 && pairs <= 74 &&
+                    flat.size() == static_cast<size_t>(pairs) * stride;
+          std::vector<int> seen(begin, 0);  // bit 0: whole, bit 1: left half, bit 2: right half
+          size_t longest = 0, shortest = 1u << 30;
+          for (int p = 0; ok && p < pairs; ++p) {
+            size_t n = 0;
+            while (n < static_cast<size_t>(stride) && flat[p * stride + n] >= 0) ++n;
+            ok = ok && n < static_cast<size_t>(stride);  // terminator inside the row
+            for (size_t i = n; ok && i < static_cast<size_t>(stride); ++i) ok = flat[p * stride + i] == -1;
+            for (size_t i = 0; ok && i < n; ++i) {
+              const int e = flat[p * stride + i], t = e & ((1 << kHalfShift) - 1), half = e >> kHalfShift;
+              ok = t < begin && half >= 0 && half <= 2 && !(seen[t] & (1 << half));
+              if (ok) seen[t] |= 1 << half;
+            }
+            longest = std::max(longest, n);
+            shortest = std::min(shortest, n);
+          }
+          for (int t = 0; ok && t < begin; ++t) {
+            const GemmProblem& pr = gp.p[(gp.nprob > 1 && t >= gp.p[1].tile_begin) ? 1 : 0];
+            const int n_blk = (t - pr.tile_begin) % pr.tiles_n;
+            const bool left_only = n_blk * BN + BN / 2 >= pr.N;
+            ok = left_only ? seen[t] == 2 : (seen[t] == 1 || seen[t] == 6);
+          }
+          ok = ok && shortest >= 1;  // only pairs with work are launched
+          if (!ok && ++bad <= 5) printf("[FAIL] sched B=%d N=%d kind=%d nsplit=%d (pairs %d stride %d)\n", B, N, kind, nsplit, pairs, stride);
+        }
+  printf("sched: %d launch shapes checked, %d failures\n", shapes, bad);
+  printf(bad ? "selftest_gemm sched: FAILED\n" : "selftest_gemm sched: ALL PASS\n");
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   std::string mode = argc > 1 ? argv[1] : "quick";
+  if (mode == "sched") return sched_selftest();
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   g_sms = prop.multiProcessorCount;
   printf("device: %s, %d SMs, cc %d.%d, smem/block optin %zu, gemm smem %zu\n", prop.name, g_sms, prop.major, prop.minor,
