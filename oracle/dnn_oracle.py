@@ -17,7 +17,7 @@ All reference paths are relative to /root/reference.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

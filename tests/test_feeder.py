@@ -70,9 +70,8 @@ def test_batches_match_the_synchronous_path(corpus, size, n):
 
 
 def same_ids(a, b):
-    """same place in the scp: un-reading across the end of the list may leave the cursor at 0 instead of len"""
-    ra, rb = a.feature_reader.reader, b.feature_reader.reader
-    return ra.scp_position % len(ra.utt_ids) == rb.scp_position % len(rb.utt_ids)
+    """exactly the same scp cursor (un-reading restores the recorded position, also across the end of the list)"""
+    return a.feature_reader.reader.scp_position == b.feature_reader.reader.scp_position
 
 
 def test_cursor_moves_survive_read_ahead(corpus):
@@ -201,8 +200,7 @@ def test_nnet_train_consumes_the_same_data_with_and_without_prefetching(corpus, 
         d = dispenser(corpus, 4)
         nnet_mod.Nnet(conf, 13, 50).train(d, prefetch=prefetch)
         logs.append(RecordingTrainer.log)
-        r = d.feature_reader.reader
-        ends.append(r.scp_position % len(r.utt_ids))
+        ends.append(d.feature_reader.reader.scp_position)
     assert logs[0] == logs[1] and ends[0] == ends[1]
     assert sum(1 for e in logs[0] if e[0] == "update") >= 14  # 2 epochs x 7 batches (+ the repeated ones)
     if 6 in losses:

@@ -5,7 +5,6 @@
 tfk_forward_posteriors call on the unpadded frames.  `loglik` additionally fuses Nnet.decode's
 host-side `np.log(output / prior)` (nnet.py:280-286) into the output kernel."""
 import numpy as np
-import torch
 
 from ..engine import Engine
 

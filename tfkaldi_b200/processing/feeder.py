@@ -22,7 +22,8 @@ import torch
 class RawBatch(object):
     """one packed batch: `utts` utterances / `frames` rows, cut into micro-batches of `utts_per_microbatch`"""
 
-    __slots__ = ("slot", "frames", "utts", "feat_dim", "mb_rows", "raw", "labels", "offsets", "cmvn", "device_slot", "on_device")
+    __slots__ = ("slot", "frames", "utts", "feat_dim", "mb_rows", "raw", "labels", "offsets", "cmvn", "device_slot", "on_device",
+                 "cursor_before")
 
     def microbatches(self):
         """(raw rows, labels, rebased utterance offsets, cmvn) views per micro-batch — device views once staged"""
@@ -56,6 +57,7 @@ class RawBatchFeeder(object):
         if self.size % self.n != 0:
             raise ValueError("the batch size (%d) must be a multiple of numutterances_per_minibatch (%d)" % (self.size, self.n))
         self.context_width = int(dispenser.feature_reader.context_width)
+        self._reader = dispenser.feature_reader.reader  # the ArkReader whose scp cursor the dispenser moves
         self.capacity = int(capacity_frames or self.size * dispenser.max_input_length)
         self.device = device
         self.depth = max(2, int(depth))
@@ -71,7 +73,7 @@ class RawBatchFeeder(object):
         self._dev = None
         self.frames_out = 0  # frames handed to the trainer so far (bench.py)
         # feature dimension of the archive: ArkReader reads by index without moving the cursor
-        self.feat_dim = int(dispenser.feature_reader.reader.read_utt_data(0).shape[1])
+        self.feat_dim = int(self._reader.read_utt_data(0).shape[1])
 
     # ------------------------------------------------------------------ host side (no CUDA needed)
     def _allocate(self):
@@ -122,8 +124,11 @@ class RawBatchFeeder(object):
                 with self._lock:
                     if self._stop:
                         return
+                    cursor = self._reader.scp_position
                     mats, stats, targets = self.dispenser.get_raw_batch()
-                    self._ready.put(self._pack(slot, mats, stats, targets))
+                    batch = self._pack(slot, mats, stats, targets)
+                    batch.cursor_before = cursor  # where the scp cursor stood before this batch was read
+                    self._ready.put(batch)
         except BaseException as exc:  # surfaced on the training thread by get()
             self._error = exc
             self._ready.put(None)
@@ -152,25 +157,28 @@ class RawBatchFeeder(object):
         self._free.put(batch.slot)
 
     def _unread(self):
-        """hand back everything that was prefetched but not consumed; returns how many batches that was.
-        Call with the lock held."""
-        n = 0
+        """hand back everything that was prefetched but not consumed: the scp cursor goes back to exactly where it
+        stood before the oldest unconsumed batch was read, i.e. where the synchronous loop would be now (the
+        dispenser's own return_batch is NOT used for this: it carries the reference's off-by-one cursor quirks,
+        processing/ark.py:144-149, which must only apply to the moves the trainer asks for).  Returns the number of
+        batches un-read.  Call with the lock held."""
+        pending = []
         if self._staged is not None:
             self._dev["copied"][self._staged.device_slot].synchronize()  # its copy may still be reading the pinned slot
-            self._free.put(self._staged.slot)
+            pending.append(self._staged)
             self._staged = None
-            n += 1
         while True:
             try:
                 batch = self._ready.get_nowait()
             except queue.Empty:
                 break
             if batch is not None:
+                pending.append(batch)
+        if pending:
+            self._reader.scp_position = pending[0].cursor_before
+            for batch in pending:
                 self._free.put(batch.slot)
-                n += 1
-        for _ in range(n):
-            self.dispenser.return_batch()
-        return n
+        return len(pending)
 
     def return_batch(self):
         """dispenser.return_batch() as seen from the trainer: one batch back from the last CONSUMED one"""
