@@ -1,0 +1,222 @@
+"""The host code above the C-ABI — Nnet.train / Nnet.decode / Trainer / Decoder / checkpoints / ark IO — end to end on
+the CPU, with tests/oracle_engine.py standing in for the CUDA engine (the GPU twin of this file is
+tests/test_gpu_nnet_e2e.py).  What is checked is ORCHESTRATION against the reference's (neuralNetworks/nnet.py:80-289,
+trainer.py:260-486, decoder.py:49-81): which engine calls are made in which order, what lands in which file, and that
+the decoded archive is what the saved weights produce — not kernel arithmetic."""
+import configparser
+import os
+
+import numpy as np
+import pytest
+
+import tfkaldi_b200.neuralNetworks.decoder as decoder_mod
+import tfkaldi_b200.neuralNetworks.trainer as trainer_mod
+from oracle_engine import HostStager, OracleEngine  # tests/oracle_engine.py (the tests directory is on sys.path)
+from tfkaldi_b200 import _lib as L
+
+NNET = """
+[directories]
+expdir = %(expdir)s
+[nnet]
+name = dnn
+context_width = 5
+num_hidden_units = 64
+num_hidden_layers = 2
+add_layer_period = %(add_layer_period)d
+starting_step = 0
+nonlin = relu
+l2_norm = False
+dropout = %(dropout)s
+batch_norm = %(batch_norm)s
+num_epochs = 2
+initial_learning_rate = 0.001
+learning_rate_decay = %(decay)s
+batch_size = 8
+numutterances_per_minibatch = 4
+valid_batches = 1
+valid_frequency = 3
+valid_adapt = %(valid_adapt)s
+valid_retries = 2
+check_freq = 4
+visualise = True
+"""
+
+
+@pytest.fixture
+def host_only(monkeypatch):
+    monkeypatch.setattr(trainer_mod, "Engine", OracleEngine)
+    monkeypatch.setattr(trainer_mod, "_Stager", HostStager)
+    monkeypatch.setattr(decoder_mod, "Engine", OracleEngine)
+    OracleEngine.calls = []
+    return OracleEngine
+
+
+def make_nnet(tmp_path, **kw):
+    from tfkaldi_b200.neuralNetworks.nnet import Nnet
+
+    opts = dict(expdir=str(tmp_path / "exp"), batch_norm="False", dropout="1", add_layer_period=0, decay="1", valid_adapt="True")
+    opts.update(kw)
+    os.makedirs(opts["expdir"], exist_ok=True)
+    conf = configparser.ConfigParser()
+    conf.read_string(NNET % opts)
+    return Nnet(conf, 40, 60)
+
+
+def corpora(tmp_path):
+    from tfkaldi_b200 import synth
+    from tfkaldi_b200.processing import batchdispenser, feature_reader, target_coder
+
+    info = synth.make_corpus(str(tmp_path / "train"), num_utts=48, min_len=20, max_len=40, feat_dim=40, num_speakers=4, num_pdfs=60, seed=0)
+    test = synth.make_corpus(str(tmp_path / "test"), num_utts=4, min_len=15, max_len=30, feat_dim=40, num_speakers=2, num_pdfs=60, seed=1, shuffle=False)
+    fd = info["featdir"]
+    reader = feature_reader.FeatureReader(fd + "/feats_shuffled.scp", fd + "/cmvn.scp", fd + "/utt2spk", 5, info["max_length"])
+    dispenser = batchdispenser.AlignmentBatchDispenser(reader, target_coder.AlignmentCoder(lambda x, y: x, 60), 8, info["alifile"])
+    treader = feature_reader.FeatureReader(test["featdir"] + "/feats.scp", test["featdir"] + "/cmvn.scp", test["featdir"] + "/utt2spk", 5, test["max_length"])
+    return dispenser, treader, test
+
+
+@pytest.mark.parametrize("batch_norm,dropout,add_layer_period", [("False", "1", 0), ("True", "0.8", 0), ("False", "1", 2)])
+def test_train_then_decode_on_the_host(host_only, tmp_path, batch_norm, dropout, add_layer_period):
+    from oracle.dnn_oracle import OracleConfig, OracleDNN
+    from tfkaldi_b200.processing import ark
+
+    dispenser, treader, test = corpora(tmp_path)
+    # random labels: the validation loss never improves.  With valid_adapt the run rolls back twice and stops
+    # (nnet.py:177-200); the layer-wise variant only reports the validation loss and trains all 12 steps.
+    adapt = add_layer_period == 0
+    nnet = make_nnet(tmp_path, batch_norm=batch_norm, dropout=dropout, add_layer_period=add_layer_period, valid_adapt=str(adapt))
+    nnet.train(dispenser, prefetch=False)
+    save = str(tmp_path / "exp" / "dnn")
+    for f in ("final.npz", "prior.npy", "training/validated.npz", "training/validated_trainvars.npz", "training/validated_optimizer.npz",
+              "logdir/loss.jsonl") + (() if adapt else ("training/step4.npz", "training/step8.npz", "training/step12.npz")):
+        assert os.path.exists(os.path.join(save, f)), f
+    assert host_only.calls.count("halve_lr") == (3 if adapt else 0)
+    # every update = 8 utterances in micro-batches of 4: accumulate, accumulate, apply (trainer.py:310-346); every
+    # validation = 8 utterances: eval_accumulate x 2, eval_finish (trainer.py:372-441)
+    calls = [c for c in host_only.calls if c != "halve_lr"]
+    i = 0
+    while i < len(calls):
+        if calls[i] == "accumulate":
+            assert calls[i:i + 3] == ["accumulate", "accumulate", "apply"], calls[i:i + 4]
+            i += 3
+        else:
+            assert calls[i:i + 3] == ["eval_accumulate", "eval_accumulate", "eval_finish"], calls[i:i + 4]
+            i += 3
+    import json
+
+    steps = [json.loads(line)["step"] for line in open(save + "/logdir/loss.jsonl")]
+    assert steps == ([0, 1, 2] * 3 if adapt else list(range(12)))  # global_step goes back with the restored trainer
+    # decode: the archive must be log(softmax/prior) of the SAVED final weights
+    decodedir = tmp_path / "decode"
+    decodedir.mkdir()
+    nnet.decode(treader, ark.ArkWriter(str(decodedir / "feats.scp"), str(decodedir / "likelihoods.ark")))
+    final = np.load(save + "/final.npz")
+    params, active = {}, 2
+    for key in final.files:
+        if key == "Classifier/initialisedlayers":
+            active = int(final[key]) + 1
+            continue
+        _, layer, rest = key.split("/", 2)
+        params[trainer_mod.MODEL_NAMES[rest] + layer[5:]] = final[key]
+    if add_layer_period:
+        assert active == 2  # grown to full depth by step 2 (1 layer at the start, +1 at step 2; 4/2 = 2 is not < 2)
+    orc = OracleDNN(OracleConfig(2, 440, 64, 60, batch_norm=batch_norm == "True", keep_prob=float(dropout)), params)
+    orc.active = active
+    prior = np.load(save + "/prior.npy")
+    out = ark.ArkReader(str(decodedir / "feats.scp"))
+    assert out.utt_ids == test["utts"]
+    from tfkaldi_b200.processing import feature_reader
+
+    again = feature_reader.FeatureReader(test["featdir"] + "/feats.scp", test["featdir"] + "/cmvn.scp", test["featdir"] + "/utt2spk", 5, test["max_length"])
+    for utt in test["utts"]:
+        uid, x, _ = again.get_utt()
+        got, want = out.read_utt(utt), orc.loglik(x, prior)
+        assert uid == utt and got.dtype == np.float32 and got.shape == want.shape
+        finite = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), finite) and np.abs(got[finite] - want[finite]).max() < 1e-5
+
+
+def test_trainer_host_logic(host_only, tmp_path):
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+
+    rng = np.random.default_rng(0)
+    dnn = DNN(30, 2, 32, act.TfActivation(act.Batchnorm(None), act.relu), True)  # layer-wise initialisation on
+    tr = CrossEnthropyTrainer(dnn, 120, 50, 50, 0.01, 0.5, 10, 2, seed=1)
+    tr.initialize()
+    assert tr.control_ops is not None and tr.engine.get_scalar(L.S_ACTIVE_LAYERS) == 1  # initialisedlayers = 0 (dnn.py:85-92)
+    x = [rng.standard_normal((t, 120)).astype(np.float32) for t in (20, 30, 25, 50)]
+    y = [rng.integers(0, 30, t).astype(np.uint32) for t in (20, 30, 25, 50)]
+    # learning rate: lr0 * decay^(global_step / num_steps), non-staircase (trainer.py:110-112)
+    for step in range(3):
+        assert tr.global_step == step and abs(tr.learning_rate() - 0.01 * 0.5 ** (step / 10.0)) < 1e-12
+        host_only.calls.clear()
+        tr.update(x, y)
+        assert host_only.calls == ["accumulate", "accumulate", "apply"]  # 4 utterances, 2 per micro-batch
+    host_only.calls.clear()
+    tr.update(x[:2], y[:2])
+    assert host_only.calls[0] == "train_step"  # exactly one micro-batch: the fused step
+    with pytest.raises(ValueError, match="multiple of numutterances_per_minibatch"):
+        tr.update(x[:3], y[:3])  # the reference's padding only works for whole micro-batches (App. A.11)
+    with pytest.raises(ValueError):
+        tr.update(x, y[:3])
+    with pytest.raises(ValueError, match="exceeds the staging capacity"):
+        tr.update([np.zeros((60, 120), np.float32), np.zeros((50, 120), np.float32)], [np.zeros(60, np.uint32), np.zeros(50, np.uint32)])
+    assert tr.evaluate(None, None) is None
+    # control ops (dnn.py:92, 114-118): add -> one more active layer (capped), init -> output layer back to zero
+    tr.control_ops["add"].run()
+    assert tr.engine.get_scalar(L.S_ACTIVE_LAYERS) == 2
+    tr.control_ops["add"].run()
+    assert tr.engine.get_scalar(L.S_ACTIVE_LAYERS) == 2
+    assert np.abs(tr.engine.get_tensor(L.T_WEIGHTS, 2)).max() > 0
+    m_before = tr.engine.get_tensor(L.T_ADAM_M_W, 2)
+    tr.control_ops["init"].run()
+    assert not tr.engine.get_tensor(L.T_WEIGHTS, 2).any() and not tr.engine.get_tensor(L.T_BIASES, 2).any()
+    assert np.array_equal(tr.engine.get_tensor(L.T_ADAM_M_W, 2), m_before)  # Adam slots are not re-initialised
+    # checkpoints: model + train variables + (superset) optimizer slots; rollback leaves the live moments alone
+    tr.halve_learning_rate()
+    path = str(tmp_path / "validated")
+    tr.save_trainer(path)
+    saved = tr.engine.dump_params()
+    arrays = np.load(path + ".npz")
+    assert int(arrays["Classifier/initialisedlayers"]) == 1  # 2 active layers
+    assert sorted(k for k in arrays.files if "layer0" in k) == [
+        "Classifier/layer0/activation/batch_norm/beta", "Classifier/layer0/activation/batch_norm/moving_mean",
+        "Classifier/layer0/activation/batch_norm/moving_variance", "Classifier/layer0/parameters/biases", "Classifier/layer0/parameters/weights"]
+    tv = np.load(path + "_trainvars.npz")
+    assert int(tv["train_variables/global_step"]) == 4 and float(tv["train_variables/learning_rate_fact"]) == 0.5
+    tr.update(x, y)
+    tr.halve_learning_rate()
+    m_live = tr.engine.get_tensor(L.T_ADAM_M_W, 0)
+    tr.restore_trainer(path)
+    assert tr.global_step == 4 and tr.engine.get_scalar(L.S_LR_FACT) == 0.5  # not 0.25: halving does not compound (App. B)
+    assert all(np.array_equal(v, saved[k]) for k, v in tr.engine.dump_params().items())
+    assert np.array_equal(tr.engine.get_tensor(L.T_ADAM_M_W, 0), m_live)  # the reference never checkpoints the moments
+    tr.restore_trainer(path, restore_optimizer=True)
+    assert not np.array_equal(tr.engine.get_tensor(L.T_ADAM_M_W, 0), m_live)
+    # the reference's own checkpoint formats restore the same way (tf_checkpoint.py)
+    tr.export_tf_checkpoint(str(tmp_path / "tfmodel"))
+    tr.update(x, y)
+    tr.restore_model(str(tmp_path / "tfmodel"))
+    assert all(np.array_equal(v, saved[k]) for k, v in tr.engine.dump_params().items())
+
+
+def test_decoder_host_logic(host_only, tmp_path):
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.decoder import Decoder
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+
+    dnn = DNN(30, 1, 32, act.TfActivation(None, act.tanh), False)
+    tr = CrossEnthropyTrainer(dnn, 120, 50, 50, 0.01, 1.0, 10, 1, seed=2)
+    tr.initialize()
+    rng = np.random.default_rng(1)
+    tr.update([rng.standard_normal((40, 120)).astype(np.float32)], [rng.integers(0, 30, 40).astype(np.uint32)])
+    tr.save_model(str(tmp_path / "final"))
+    dec = Decoder(dnn, 120, 50)
+    dec.restore(str(tmp_path / "final"))
+    x = rng.standard_normal((17, 120)).astype(np.float32)
+    post = dec(x)  # decoder.py:49-71: [T, O] softmax posteriors of the unpadded utterance
+    assert post.shape == (17, 30) and post.dtype == np.float32 and np.abs(post.sum(1) - 1).max() < 1e-5
+    assert np.allclose(post, tr.engine.orc.posteriors(x), atol=1e-7)
