@@ -182,7 +182,9 @@ class OracleDNN:
         """CrossEnthropyTrainer.compute_loss (trainer.py:514-531): SUM over frames of
         softmax_cross_entropy_with_logits(logits, one_hot(labels)); returns (loss_sum, dlogits)
         with dlogits = softmax - onehot (not divided by the frame count).
-        Labels outside [0,O) give an all-zero one-hot row (tf.one_hot) => loss 0, gradient 0."""
+        Labels outside [0,O) give an all-zero one-hot row (tf.one_hot) => loss 0; the gradient of that row is still
+        softmax - onehot = softmax (the TF op computes backprop = prob - labels whatever the labels sum to).  Cannot
+        occur through the reference's data path (alignments are < num_labels), kept for literal fidelity."""
         z = logits.astype(F32, copy=False)
         mx = z.max(axis=1, keepdims=True)
         e = np.exp(z - mx)
@@ -194,8 +196,7 @@ class OracleDNN:
         row_loss = (np.log(s[:, 0]) + mx[:, 0] - z[rows, idx]).astype(F32, copy=False)
         row_loss = np.where(ok, row_loss, F32(0))
         d = (e / s).astype(F32, copy=False)
-        d[rows, idx] -= F32(1)
-        d[~ok] = 0
+        d[rows[ok], labels[ok]] -= F32(1)
         return float(row_loss.sum(dtype=np.float64)), d.astype(F32, copy=False)
 
     # ------------------------------------------------------------------ backward

@@ -143,7 +143,7 @@ def test_single_step_gradients(cuda_device, variant):
     if cfg.l2_norm:
         x[::2] *= 3  # drive some frames above mean square 1: both L2Norm branches
     y = rng.integers(0, 183, B)
-    y[5] = 183  # out-of-range label: empty one-hot row (tf.one_hot) -> no loss, no gradient
+    y[5] = 183  # out-of-range label: empty one-hot row (tf.one_hot) -> no loss term, gradient softmax - 0
     eng.set_dropout_seed(77)
     eng.accumulate(x, y)
     orc.accumulate(x, y, dropout_seed=77)

@@ -199,3 +199,18 @@ def test_microbatch_accumulation_equals_one_big_batch_without_bn():
     for k in a.grads:
         assert np.allclose(a.grads[k], b.grads[k], atol=1e-5)
     assert abs(a.apply(1e-3) - b.apply(1e-3)) < 1e-6
+
+
+def test_out_of_range_label_follows_the_tensorflow_op():
+    """tf.one_hot gives an all-zero row for a label outside [0, O); softmax_cross_entropy_with_logits then contributes
+    no loss, but its registered gradient is grad * (prob - labels) = softmax for that frame (trainer.py:526-531).
+    Cannot occur through the reference's data path; restated literally."""
+    from oracle.dnn_oracle import OracleDNN
+
+    z = np.array([[0.0, 1.0, 2.0], [1.0, 1.0, 1.0], [3.0, 0.0, -1.0]], np.float32)
+    loss, d = OracleDNN.softmax_ce(z, np.array([2, 3, -1]))
+    p = np.exp(z - z.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    assert abs(loss - (-np.log(p[0, 2]))) < 1e-6  # only the first frame has a loss term
+    assert np.allclose(d[0], p[0] - np.array([0, 0, 1]), atol=1e-7)
+    assert np.allclose(d[1], p[1], atol=1e-7) and np.allclose(d[2], p[2], atol=1e-7)

@@ -191,8 +191,9 @@ softmax_ce_kernel(const float* __restrict__ logits, int ld, const int32_t* __res
     if (idx >= nvec) continue;
     const int e = idx << 2;
     float p[4] = {z[i].x * inv, z[i].y * inv, z[i].z * inv, z[i].w * inv};
-    if (!label_ok) p[0] = p[1] = p[2] = p[3] = 0.f;
-    else if ((label >> 2) == idx) p[label & 3] -= 1.0f;
+    // softmax - onehot; an out-of-range label has an all-zero one-hot row (tf.one_hot): no loss term, but the op's
+    // gradient is still prob - labels = softmax (SoftmaxCrossEntropyWithLogits computes backprop = prob - labels)
+    if (label_ok && (label >> 2) == idx) p[label & 3] -= 1.0f;
     uint2 h, l;
     split2(p[0], p[1], h.x, l.x);
     split2(p[2], p[3], h.y, l.y);
@@ -223,7 +224,7 @@ softmax_ce_generic_kernel(const float* __restrict__ logits, int ld, const int32_
   if (d_hi == nullptr) return;
   const float inv = 1.0f / sum;
   for (int e = lane; e < ld; e += 32) {
-    float p = (e < O && label_ok) ? expf(zp[e] - mx) * inv : 0.f;
+    float p = e < O ? expf(zp[e] - mx) * inv : 0.f;
     if (label_ok && e == label) p -= 1.0f;
     const __nv_bfloat16 h = __float2bfloat16_rn(p);
     d_hi[static_cast<size_t>(row) * ld + e] = h;

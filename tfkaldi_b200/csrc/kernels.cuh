@@ -34,7 +34,8 @@ int k_double_to_float(const double* src, float* dst, cudaStream_t st);
 
 // Softmax cross-entropy forward+backward in one pass over the logits
 // (reference: neuralNetworks/trainer.py:526-531: one_hot + softmax_cross_entropy_with_logits + reduce_sum).
-//   row_loss[r] = logsumexp(z_r) - z_r[label_r]        (0 if the label is outside [0,O): empty one-hot row)
+//   row_loss[r] = logsumexp(z_r) - z_r[label_r]        (0 if the label is outside [0,O): empty one-hot row; the
+//                                                       gradient of such a row is softmax - 0, as TensorFlow's op gives)
 //   d = softmax(z_r) - onehot(label_r)  -> bf16 hi (+lo), pad columns [O, ld) zeroed.  d_hi may be null.
 int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int O, float* row_loss,
                  __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, cudaStream_t st);
