@@ -66,6 +66,10 @@ extern "C" {
 #define TFK_S_ACTIVE_LAYERS 2 /* Classifier/initialisedlayers + 1   (classifiers/dnn.py:85-89) */
 #define TFK_S_LOSS_SUM 3      /* batch_loss accumulator             (trainer.py:91-93), read-only */
 #define TFK_S_NUM_FRAMES 4    /* train/num_frames accumulator       (trainer.py:126-128), read-only */
+#define TFK_S_ADAM_STEP 5     /* Adam's own step count t (TF: beta1_power/beta2_power inside AdamOptimizer, trainer.py:115).
+                                 Advanced by every tfk_apply / tfk_train_step, NOT touched by setting TFK_S_GLOBAL_STEP:
+                                 the reference's `train_variables` saver (trainer.py:204-205) does not hold the beta powers,
+                                 so a restored / rolled-back trainer keeps counting and a freshly initialised one restarts at 0 */
 
 typedef struct tfk_handle tfk_handle;
 
@@ -181,8 +185,14 @@ int tfk_halve_lr(tfk_handle* h);
 /* == control_ops['add'] (classifiers/dnn.py:92): use the first n hidden layers, 1 <= n <= L */
 int tfk_set_active_layers(tfk_handle* h, int n);
 /* Philox key for the NEXT tfk_accumulate's dropout masks (layer l uses seed + l); afterwards the
- * engine advances it by num_layers + 1 per call. */
+ * engine advances it by num_layers + 1 per call.  Under data parallelism a rank is one micro-batch of the step
+ * (trainer.py:310-332): rank r uses seed + r (num_layers + 1) + l and a call advances it by nranks (num_layers + 1),
+ * the sequence one GPU accumulating the ranks' shards as micro-batches would draw. */
 int tfk_set_dropout_seed(tfk_handle* h, uint64_t seed);
+/* Diagnostic read-back (tests): the stored output of hidden layer `layer` from the LAST forward pass — what the
+ * backward pass derives the ReLU / dropout gradient mask from (activation.py:84, 140-141) — as fp32 [B, hidden_dim]
+ * into the DEVICE buffer dst.  Lets a checker replay the backward pass with exactly the engine's activation pattern. */
+int tfk_get_activation(tfk_handle* h, int layer, float* dst, int B, void* stream);
 
 /* Data parallel (no reference equivalent: a rank plays the role of one utterance micro-batch of
  * trainer.py:310-332).  tfk_comm_unique_id: rank 0 fills 128 bytes; every rank then calls

@@ -113,6 +113,10 @@ class OracleDNN:
         self.loss_sum = 0.0  # batch_loss        trainer.py:91-93
         self.num_frames = 0  # train/num_frames  trainer.py:126-128
         self.global_step = 0  # trainer.py:98-100
+        # Adam's own step count: tf.train.AdamOptimizer keeps beta1_power / beta2_power as optimizer variables
+        # (trainer.py:115); they are initialised by init_op and are NOT in the `train_variables` saver
+        # (trainer.py:204-205), so restore_trainer rewinds global_step but never the beta powers
+        self.adam_step = 0
         self.lr_fact = 1.0  # trainer.py:104-106
 
     # ------------------------------------------------------------------ forward
@@ -200,8 +204,13 @@ class OracleDNN:
         return float(row_loss.sum(dtype=np.float64)), d.astype(F32, copy=False)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, caches, dlogits: np.ndarray) -> dict:
-        """tf.gradients(loss, params) (trainer.py:155), written out.  Returns {name: grad}."""
+    def backward(self, caches, dlogits: np.ndarray, relu_pass=None) -> dict:
+        """tf.gradients(loss, params) (trainer.py:155), written out.  Returns {name: grad}.
+
+        relu_pass (test aid): optional list of boolean [B, N] arrays, one per hidden layer, used INSTEAD of this
+        implementation's own `a > 0` as the ReLU gradient gate (activation.py:84).  A pre-activation within rounding
+        distance of zero lands on either side in any two fp32 implementations; replaying the backward pass with the
+        other implementation's activation pattern takes that discontinuity out of a gradient comparison."""
         cfg = self.cfg
         g = {}
         L = self.L
@@ -222,7 +231,7 @@ class OracleDNN:
                 dn = dh / c.sig - c.a * (F32(2) * dot / (n * c.sig * c.sig))
                 dh = np.where(c.sig > 1, dn, dh).astype(F32, copy=False)
             if cfg.nonlin == "relu":
-                dh = np.multiply(dh, c.a > 0, dtype=F32)
+                dh = np.multiply(dh, (c.a > 0) if relu_pass is None else relu_pass[l], dtype=F32)
             elif cfg.nonlin == "sigmoid":
                 dh = (dh * (c.a * (F32(1) - c.a))).astype(F32, copy=False)
             elif cfg.nonlin == "tanh":
@@ -242,11 +251,11 @@ class OracleDNN:
         return g
 
     # ------------------------------------------------------------------ trainer steps
-    def accumulate(self, x, labels, dropout_seed: int = 0) -> float:
+    def accumulate(self, x, labels, dropout_seed: int = 0, relu_pass=None) -> float:
         """== update_gradients_op.run(feed) (trainer.py:165-169, 328): one micro-batch."""
         logits, caches = self.forward(x, training=True, dropout_seed=dropout_seed)
         loss, d = self.softmax_ce(logits, labels)
-        g = self.backward(caches, d)
+        g = self.backward(caches, d, relu_pass=relu_pass)
         for k, v in g.items():
             self.grads[k] += v  # grads[p].assign_add(batchgrads[p])
         self.loss_sum += loss  # batch_loss.assign_add(loss)
@@ -264,7 +273,8 @@ class OracleDNN:
         cfg = self.cfg
         mean_loss = self.loss_sum / float(self.num_frames)
         self.global_step += 1
-        t = float(self.global_step)
+        self.adam_step += 1
+        t = float(self.adam_step)
         b1, b2 = cfg.adam_beta1, cfg.adam_beta2
         lr_t = F32(lr * self.lr_fact * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
         nf = F32(self.num_frames)

@@ -59,6 +59,8 @@ class OracleEngine(object):
     def set_scalar(self, kind, value):
         if kind == L.S_GLOBAL_STEP:
             self.orc.global_step = int(value)
+        elif kind == L.S_ADAM_STEP:
+            self.orc.adam_step = int(value)
         elif kind == L.S_LR_FACT:
             self.orc.lr_fact = float(value)
         else:
@@ -67,7 +69,7 @@ class OracleEngine(object):
     def get_scalar(self, kind):
         o = self.orc
         return float({L.S_GLOBAL_STEP: o.global_step, L.S_LR_FACT: o.lr_fact, L.S_ACTIVE_LAYERS: o.active, L.S_LOSS_SUM: o.loss_sum,
-                      L.S_NUM_FRAMES: o.num_frames}[kind])
+                      L.S_NUM_FRAMES: o.num_frames, L.S_ADAM_STEP: o.adam_step}[kind])
 
     def load_params(self, params):
         for key, val in params.items():

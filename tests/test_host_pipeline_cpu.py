@@ -220,3 +220,51 @@ def test_decoder_host_logic(host_only, tmp_path):
     post = dec(x)  # decoder.py:49-71: [T, O] softmax posteriors of the unpadded utterance
     assert post.shape == (17, 30) and post.dtype == np.float32 and np.abs(post.sum(1) - 1).max() < 1e-5
     assert np.allclose(post, tr.engine.orc.posteriors(x), atol=1e-7)
+
+
+def test_adam_step_count_survives_restore_and_restarts_on_initialize(host_only, tmp_path):
+    """tf.train.AdamOptimizer keeps beta1_power / beta2_power inside the optimizer (trainer.py:115); the
+    `train_variables` saver holds global_step and learning_rate_fact only (trainer.py:204-205).  So
+      * a validation rollback (restore_trainer, nnet.py:184-187) rewinds global_step but Adam keeps counting;
+      * a resumed run (initialize() then restore_trainer(step N), nnet.py:134-140) restarts Adam at t = 1 with zero
+        moments — NOT at t = N + 1, whose bias correction ~1 would make the first updates several times too large."""
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+
+    def trainer():
+        dnn = DNN(11, 2, 16, act.TfActivation(None, act.relu), False)
+        tr = CrossEnthropyTrainer(dnn, 24, 50, 50, 1e-3, 1.0, 100, 1, seed=3)
+        tr.initialize()
+        return tr
+
+    rng = np.random.default_rng(0)
+    x = [rng.standard_normal((30, 24)).astype(np.float32)]
+    y = [rng.integers(0, 11, 30).astype(np.uint32)]
+    tr = trainer()
+    for _ in range(5):
+        tr.update(x, y)
+    assert tr.global_step == 5 and tr.engine.get_scalar(L.S_ADAM_STEP) == 5
+    tr.save_trainer(str(tmp_path / "step5"))
+    for _ in range(3):
+        tr.update(x, y)
+    tr.restore_trainer(str(tmp_path / "step5"))  # rollback: global_step back to 5, Adam's t stays at 8
+    assert tr.global_step == 5 and tr.engine.get_scalar(L.S_ADAM_STEP) == 8
+    w_before = tr.engine.get_tensor(L.T_WEIGHTS, 2).copy()
+    tr.update(x, y)
+    assert tr.engine.get_scalar(L.S_ADAM_STEP) == 9
+
+    fresh = trainer()  # resume in a new process: init_op, then restore_trainer
+    fresh.restore_trainer(str(tmp_path / "step5"))
+    assert fresh.global_step == 5 and fresh.engine.get_scalar(L.S_ADAM_STEP) == 0
+    assert not fresh.engine.get_tensor(L.T_ADAM_M_W, 2).any()
+    w0 = fresh.engine.get_tensor(L.T_WEIGHTS, 2).copy()
+    fresh.update(x, y)
+    step = np.abs(fresh.engine.get_tensor(L.T_WEIGHTS, 2) - w0).max()
+    # Adam's first step from zero moments with t = 1 moves every weight by at most lr (sign-like); with t = 6 and
+    # zero moments it would be lr * sqrt(1-b2^6)/(1-b1^6) * 0.1/sqrt(0.001) = 0.52 lr ... and at t >> 1 3.2 lr
+    assert step <= 1.0001e-3, step
+    full = trainer()  # restore_optimizer=True brings moments AND the step count back (superset of the reference)
+    full.restore_trainer(str(tmp_path / "step5"), restore_optimizer=True)
+    assert full.engine.get_scalar(L.S_ADAM_STEP) == 5 and full.engine.get_tensor(L.T_ADAM_V_W, 2).any()
+    del w_before

@@ -19,7 +19,7 @@ TFK_NONLIN_RELU, TFK_NONLIN_LINEAR, TFK_NONLIN_SIGMOID, TFK_NONLIN_TANH = 0, 1, 
 
 (T_WEIGHTS, T_BIASES, T_BN_BETA, T_BN_MOVING_MEAN, T_BN_MOVING_VAR, T_ADAM_M_W, T_ADAM_V_W, T_ADAM_M_B,
  T_ADAM_V_B, T_ADAM_M_BETA, T_ADAM_V_BETA, T_GRAD_W, T_GRAD_B, T_GRAD_BETA) = range(14)
-S_GLOBAL_STEP, S_LR_FACT, S_ACTIVE_LAYERS, S_LOSS_SUM, S_NUM_FRAMES = range(5)
+S_GLOBAL_STEP, S_LR_FACT, S_ACTIVE_LAYERS, S_LOSS_SUM, S_NUM_FRAMES, S_ADAM_STEP = range(6)
 TIMER_NAMES = ["gemm_fwd", "gemm_bwd", "softmax_ce", "adam", "colsum", "bn", "convert", "decode_out", "allreduce"]
 NUM_TIMERS = len(TIMER_NAMES)
 
@@ -76,6 +76,7 @@ SIGNATURES = [
     ("tfk_halve_lr", C.c_int, [_H]),
     ("tfk_set_active_layers", C.c_int, [_H, C.c_int]),
     ("tfk_set_dropout_seed", C.c_int, [_H, C.c_uint64]),
+    ("tfk_get_activation", C.c_int, [_H, C.c_int, _FP, C.c_int, C.c_void_p]),
     ("tfk_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("tfk_comm_init", C.c_int, [_H, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
     ("tfk_set_comm", C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),

@@ -82,6 +82,7 @@ struct Layer {
   size_t off_w = 0, off_b = 0, off_beta = 0;  // offsets (floats) into the parameter arenas
   size_t w_count = 0;                         // floats reserved for W (K*ldn rounded up to 1024)
   bool peer_reduce = false;                   // wgrad epilogue adds straight into the owner GPU's slice
+  CUtensorMap* peer_tm = nullptr;             // device [nranks]: every rank's copy of this layer's gradient matrix
   float *moving_mean = nullptr, *moving_var = nullptr;  // [npad]
   float *bn_mean = nullptr, *bn_rstd = nullptr;          // statistics used by the last forward
   float* bn_sums = nullptr;                              // [2*ldn] backward column sums
@@ -139,6 +140,9 @@ struct tfk_handle {
   std::map<std::vector<int>, TileLists> list_cache;  // CTA-pair work lists per launch shape (finish_params)
   // trainer scalars
   long long global_step = 0;
+  // Adam's own step count t (TF keeps beta1_power / beta2_power inside the optimizer: they are NOT in the
+  // `train_variables` saver, so restore_trainer never rewinds them and init_op resets them; trainer.py:115,204-205)
+  long long adam_step = 0;
   double lr_fact = 1.0;
   unsigned long long drop_seed = 0;
   // DP
@@ -150,6 +154,12 @@ struct tfk_handle {
   std::vector<cudaEvent_t> layer_events;
   std::vector<cudaEvent_t> colsum_events;  // tfk_train_step: column sums of layer l taken (side stream)
   int pending_accumulates = 0;             // tfk_accumulate calls since the last tfk_apply
+  // data parallel: the host may queue at most `runahead` optimizer steps ahead of the device (TFK_DP_RUNAHEAD,
+  // default 2, 0 = unbounded).  Ranks whose hosts run many steps ahead of each other keep NCCL work, peer stores
+  // and flag waits of different steps in flight at once; bounding it costs nothing (the device stays 2 steps deep).
+  int runahead = 2;
+  std::vector<cudaEvent_t> step_events;
+  long long steps_queued = 0;
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   // timers
   bool timers_on = false;
@@ -285,14 +295,7 @@ int finish_params(tfk_handle* h, Plan& plan, const GemmSpec* s, int n, GemmParam
   return TFK_OK;
 }
 
-void free_plan(Plan& plan) {
-  for (auto& gp : plan.bwd)
-    for (int i = 0; i < 2; ++i)
-      if (gp.p[i].peer_tm) {
-        cudaFree(const_cast<CUtensorMap*>(gp.p[i].peer_tm));
-        gp.p[i].peer_tm = nullptr;
-      }
-}
+void free_plan(Plan& plan) { (void)plan; }  // plans hold host-side tensor maps only; device lists / peer maps are the handle's
 
 int build_plan(tfk_handle* h, int B, Plan& plan) {
   const int L = h->L, act = h->active;
@@ -361,10 +364,8 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       if (ks > kb / 16) ks = kb / 16;
       s[0].ksplit = ks < 1 ? 1 : ks;
     }
-    std::vector<void*> peers;
     if (h->fused_rs && ly.peer_reduce) {  // add each output slab into its owner GPU's accumulator over NVLink
-      for (int r = 0; r < h->nranks; ++r) peers.push_back(h->peer_G[r] + ly.off_w);
-      s[0].peer_D = peers.data();
+      s[0].peer_tm = ly.peer_tm;
       s[0].num_peers = h->nranks;
       s[0].rows_per_owner = ly.K / h->nranks;
     }
@@ -436,6 +437,16 @@ int check_frames(tfk_handle* h, int B, const char* what) {
   return TFK_OK;
 }
 
+// Philox key of layer l's dropout mask in the micro-batch about to run.  `drop_seed` counts GLOBAL micro-batches:
+// K data-parallel ranks stand for K accumulated micro-batches of one step (trainer.py:310-332), micro-batch j of
+// which uses drop_seed + j (L+1); rank r is micro-batch r, so every rank draws a different mask.
+inline unsigned long long layer_seed(const tfk_handle* h, int l) {
+  return h->drop_seed + static_cast<unsigned long long>(h->rank) * (h->L + 1) + static_cast<unsigned long long>(l);
+}
+inline void advance_drop_seed(tfk_handle* h) {
+  h->drop_seed += static_cast<unsigned long long>(h->nranks) * (h->L + 1);
+}
+
 // forward of hidden layers [first, active) and optionally the output layer; input must be in act[first]
 int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bool with_output,
                   cudaStream_t st) {
@@ -447,7 +458,7 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
     if (l == L && !with_output) break;
     Layer& ly = h->layers[l];
     GemmParams gp = training ? plan.fwd_train[l] : plan.fwd_eval[l];
-    if (training && gp.p[0].drop_thr != 0u) gp.p[0].seed = h->drop_seed + static_cast<unsigned long long>(l);
+    if (training && gp.p[0].drop_thr != 0u) gp.p[0].seed = layer_seed(h, l);
     {
       TimerScope ts(h, st, TFK_TIMER_GEMM_FWD);
       TFK_LAUNCH(h, gemm_launch(gp, h->num_sms, st));
@@ -464,13 +475,13 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
       const bool l2 = h->cfg.l2_norm != 0;
       const float keep = (!l2 && training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
       TFK_LAUNCH(h, k_bn_apply(ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd, h->P + ly.off_beta,
-                               act_code, keep, h->drop_seed + static_cast<unsigned long long>(l),
+                               act_code, keep, layer_seed(h, l),
                                l2 ? ly.u_hi : h->act_hi[l + 1], l2 ? ly.u_lo : h->act_lo[l + 1], st));
     }
     if (ly.hidden && h->cfg.l2_norm) {
       TimerScope ts(h, st, TFK_TIMER_BN);
       const float keep = (training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
-      TFK_LAUNCH(h, k_l2norm_fwd(ly.u_hi, ly.u_lo, ly.ldn, B, ly.N, keep, h->drop_seed + static_cast<unsigned long long>(l),
+      TFK_LAUNCH(h, k_l2norm_fwd(ly.u_hi, ly.u_lo, ly.ldn, B, ly.N, keep, layer_seed(h, l),
                                  h->act_hi[l + 1], h->act_lo[l + 1], ly.l2_s, st));
     }
   }
@@ -749,6 +760,7 @@ int tfk_destroy(tfk_handle* h) {
   if (h->adam_stream) cudaStreamDestroy(h->adam_stream);
   for (auto e : h->layer_events) cudaEventDestroy(e);
   for (auto e : h->colsum_events) cudaEventDestroy(e);
+  for (auto e : h->step_events) cudaEventDestroy(e);
   for (auto& kv : h->plans) free_plan(kv.second);
   for (auto& kv : h->list_cache) cudaFree(kv.second.d);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -788,6 +800,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
   h->x3 = cfg->precision == TFK_PREC_BF16X3;
   h->drop_seed = cfg->seed;
   if (const char* e = getenv("TFK_GEMM_2CTA")) h->two_cta = atoi(e) != 0;
+  if (const char* e = getenv("TFK_DP_RUNAHEAD")) h->runahead = atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
   auto bail = [&](int rc) {
     g_create_error = h->err;
     tfk_destroy(h);
@@ -948,6 +961,7 @@ int tfk_set_scalar(tfk_handle* h, int kind, double value) {
   if (!h) return TFK_EINVAL;
   switch (kind) {
     case TFK_S_GLOBAL_STEP: h->global_step = static_cast<long long>(value); return TFK_OK;
+    case TFK_S_ADAM_STEP: h->adam_step = static_cast<long long>(value); return TFK_OK;
     case TFK_S_LR_FACT: h->lr_fact = value; return TFK_OK;
     case TFK_S_ACTIVE_LAYERS: return tfk_set_active_layers(h, static_cast<int>(value));
     default: return fail(h, TFK_EINVAL, "tfk_set_scalar: kind %d is not writable", kind);
@@ -958,6 +972,7 @@ int tfk_get_scalar(tfk_handle* h, int kind, double* value_host, void* stream) {
   if (!h || !value_host) return fail(h, TFK_EINVAL, "tfk_get_scalar: null argument");
   switch (kind) {
     case TFK_S_GLOBAL_STEP: *value_host = static_cast<double>(h->global_step); return TFK_OK;
+    case TFK_S_ADAM_STEP: *value_host = static_cast<double>(h->adam_step); return TFK_OK;
     case TFK_S_LR_FACT: *value_host = h->lr_fact; return TFK_OK;
     case TFK_S_ACTIVE_LAYERS: *value_host = h->active; return TFK_OK;
     case TFK_S_LOSS_SUM:
@@ -1122,7 +1137,7 @@ int tfk_accumulate(tfk_handle* h, const float* x, const int32_t* labels, int B, 
   TFK_TRY(load_input(h, x, B, 0, st));
   TFK_TRY(forward_range(h, *plan, B, true, 0, true, st));
   TFK_TRY(ce_and_backward(h, *plan, labels, B, true, st));
-  h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  advance_drop_seed(h);
   h->pending_accumulates += 1;
   return TFK_OK;
 }
@@ -1155,7 +1170,7 @@ int tfk_accumulate_raw(tfk_handle* h, const float* raw, const int32_t* utt_offse
   TFK_TRY(load_raw(h, raw, utt_offsets, num_utts, cmvn, feat_dim, context, 0, R, st));
   TFK_TRY(forward_range(h, *plan, R, true, 0, true, st));
   TFK_TRY(ce_and_backward(h, *plan, labels, R, true, st));
-  h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  advance_drop_seed(h);
   h->pending_accumulates += 1;
   return TFK_OK;
 }
@@ -1194,7 +1209,8 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (h->sharded) TFK_TRY(reduce_scatter_grads(h, st));
   else TFK_TRY(allreduce_grads(h, st));
   h->global_step += 1;  // apply_gradients(global_step=...)   trainer.py:182-184
-  const double t = static_cast<double>(h->global_step);
+  h->adam_step += 1;    // beta1_power / beta2_power advance with every apply, whatever global_step is restored to
+  const double t = static_cast<double>(h->adam_step);
   const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
   const double lr_eff = static_cast<double>(lr) * h->lr_fact;
   const float lr_t = static_cast<float>(lr_eff * std::sqrt(1.0 - std::pow(b2, t)) / (1.0 - std::pow(b1, t)));
@@ -1246,6 +1262,15 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (mean_loss_host) {
     TFK_CUDA(h, cudaStreamSynchronize(st));
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);  // average_loss   trainer.py:198
+  } else if (h->comm && h->nranks > 1 && h->runahead > 0) {
+    if (h->step_events.empty()) {
+      h->step_events.resize(h->runahead);
+      for (auto& e : h->step_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaEvent_t e = h->step_events[h->steps_queued % h->runahead];
+    if (h->steps_queued >= h->runahead) TFK_CUDA(h, cudaEventSynchronize(e));  // step (k - runahead) has finished
+    TFK_CUDA(h, cudaEventRecord(e, st));
+    h->steps_queued += 1;
   }
   return TFK_OK;
 }
@@ -1272,7 +1297,8 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
     TFK_LAUNCH(h, k_accum_loss(h->row_loss, B, h->acc, st));  // acc = {loss_sum, frames}: Adam reads frames
   }
   h->global_step += 1;
-  const double t = static_cast<double>(h->global_step);
+  h->adam_step += 1;
+  const double t = static_cast<double>(h->adam_step);
   const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
   const float lr_t = static_cast<float>(static_cast<double>(lr) * h->lr_fact * std::sqrt(1.0 - std::pow(b2, t)) /
                                         (1.0 - std::pow(b1, t)));
@@ -1321,7 +1347,7 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
     TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, off, cnt, n, h->acc, lr_t,
                          h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
   }
-  h->drop_seed += static_cast<unsigned long long>(h->L + 1);
+  advance_drop_seed(h);
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));
   if (mean_loss_host) {
@@ -1383,6 +1409,14 @@ int tfk_eval_finish(tfk_handle* h, float* mean_loss_host, void* stream) {
   if (!h || !mean_loss_host) return fail(h, TFK_EINVAL, "tfk_eval_finish: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (h->comm && h->nranks > 1) {
+    // data parallel: every rank holds a different share of the validation utterances; the decisions Nnet.train
+    // takes on this number (rollback, halving, stop: nnet.py:168-207) must be identical on all ranks
+    NcclApi& api = nccl();
+    TimerScope ts(h, st, TFK_TIMER_ALLREDUCE);
+    const int rc = api.AllReduce(h->acc, h->acc, 2, kNcclDouble, kNcclSum, h->comm, st);
+    if (rc) return fail(h, TFK_ENCCL, "ncclAllReduce (validation loss) failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+  }
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));
   TFK_CUDA(h, cudaStreamSynchronize(st));
@@ -1421,6 +1455,18 @@ int tfk_forward_posteriors(tfk_handle* h, const float* x, int T, float* out, voi
 int tfk_forward_loglik(tfk_handle* h, const float* x, int T, const float* prior, float* out, void* stream) {
   if (!h || !x || !out || !prior) return fail(h, TFK_EINVAL, "tfk_forward_loglik: null argument");
   return forward_decode(h, x, T, prior, out, static_cast<cudaStream_t>(stream));
+}
+
+int tfk_get_activation(tfk_handle* h, int layer, float* dst, int B, void* stream) {
+  if (!h || !dst) return fail(h, TFK_EINVAL, "tfk_get_activation: null argument");
+  if (layer < 0 || layer >= h->L) return fail(h, TFK_EINVAL, "tfk_get_activation: hidden layer %d of %d", layer, h->L);
+  TFK_TRY(check_frames(h, B, "tfk_get_activation"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TFK_CUDA(h, cudaSetDevice(h->cfg.device));
+  const Layer& ly = h->layers[layer];
+  TimerScope ts(h, st, TFK_TIMER_CONVERT);
+  TFK_LAUNCH(h, k_merge_bf16(h->act_hi[layer + 1], h->act_lo[layer + 1], ly.ldn, dst, ly.N, B, ly.N, st));
+  return TFK_OK;
 }
 
 int tfk_comm_unique_id(uint8_t* id128_host) {
@@ -1525,6 +1571,14 @@ int tfk_ipc_import(tfk_handle* h, const uint8_t* handles_host, int nranks) {
     ly.peer_reduce = ly.K % nranks == 0 && (ly.K / nranks) % 32 == 0 &&
                      ly.w_count == static_cast<size_t>(ly.K) * ly.ldn;
     eligible += ly.peer_reduce ? 1 : 0;
+    if (ly.peer_reduce && !ly.peer_tm) {  // per layer, once: the maps do not depend on the frame count
+      std::vector<void*> peers;
+      for (int r = 0; r < nranks; ++r) peers.push_back(h->peer_G[r] + ly.off_w);
+      char err[256] = {0};
+      if (gemm_build_peer_maps(peers.data(), nranks, ly.K, ly.N, ly.ldn, &ly.peer_tm, err, sizeof(err)))
+        return fail(h, TFK_ECUDA, "tfk_ipc_import layer %d: %s", l, err);
+      h->allocs.push_back(ly.peer_tm);
+    }
   }
   const char* mode = getenv("TFK_DP_MODE");
   const bool nccl_only = mode && strcmp(mode, "sharded_nccl") == 0;

@@ -802,6 +802,26 @@ int gemm_init() {
   return 0;
 }
 
+int gemm_build_peer_maps(void* const* peer_D, int num_peers, int M, int N, int ldd, CUtensorMap** d_out, char* err,
+                         int errlen) {
+  *d_out = nullptr;
+  std::vector<CUtensorMap> maps(num_peers);
+  for (int o = 0; o < num_peers; ++o) {
+    const int rc = make_tmap(&maps[o], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, peer_D[o], N, M, ldd, 32, 32, err, errlen);
+    if (rc) return rc;
+  }
+  CUtensorMap* d = nullptr;
+  cudaError_t ce = cudaMalloc(&d, maps.size() * sizeof(CUtensorMap));
+  if (ce == cudaSuccess) ce = cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    snprintf(err, errlen, "peer tensor-map upload failed: %s", cudaGetErrorString(ce));
+    if (d) cudaFree(d);
+    return -2;
+  }
+  *d_out = d;
+  return 0;
+}
+
 int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* out, char* err,
                       int errlen, int two_cta) {
   if (nspec < 1 || nspec > 2) {
@@ -892,25 +912,12 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.peer_tm = nullptr;
     p.num_peers = 0;
     p.rows_per_owner = 0;
-    if (s.peer_D != nullptr && s.num_peers > 1) {
+    if (s.peer_tm != nullptr && s.num_peers > 1) {
       if (s.out_kind != OUT_F32_REDADD || s.rows_per_owner <= 0 || s.rows_per_owner % 32 != 0) {
         snprintf(err, errlen, "gemm: peer reduce needs OUT_F32_REDADD and rows_per_owner %% 32 == 0");
         return -1;
       }
-      std::vector<CUtensorMap> maps(s.num_peers);
-      for (int o = 0; o < s.num_peers; ++o) {
-        rc = make_tmap(&maps[o], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s.peer_D[o], s.N, s.M, s.ldd, 32, 32, err, errlen);
-        if (rc) return rc;
-      }
-      CUtensorMap* d = nullptr;
-      cudaError_t ce = cudaMalloc(&d, maps.size() * sizeof(CUtensorMap));
-      if (ce == cudaSuccess) ce = cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
-      if (ce != cudaSuccess) {
-        snprintf(err, errlen, "peer tensor-map upload failed: %s", cudaGetErrorString(ce));
-        if (d) cudaFree(d);
-        return -2;
-      }
-      p.peer_tm = d;
+      p.peer_tm = s.peer_tm;
       p.num_peers = s.num_peers;
       p.rows_per_owner = s.rows_per_owner;
     }

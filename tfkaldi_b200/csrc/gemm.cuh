@@ -78,9 +78,9 @@ struct GemmSpec {
   float* colsum_part = nullptr;
   int colsum_ld = 0;
   // OUT_F32_REDADD only: fused reduce-scatter.  Output rows [o*rows_per_owner, (o+1)*rows_per_owner) are
-  // reduce-added into peer_D[o] (the same [M, ldd] matrix on GPU o, mapped over NVLink; the local pointer
-  // for this rank) instead of D_hi.  rows_per_owner must be a multiple of 32.
-  void* const* peer_D = nullptr;
+  // reduce-added through peer_tm[o] (tensor map of the same [M, ldd] matrix on GPU o, mapped over NVLink; the
+  // local matrix for this rank) instead of D_hi.  rows_per_owner must be a multiple of 32.
+  const CUtensorMap* peer_tm = nullptr;  // DEVICE array [num_peers] from gemm_build_peer_maps (depends on the matrix only)
   int num_peers = 0;
   int rows_per_owner = 0;
 };
@@ -107,7 +107,7 @@ struct alignas(64) GemmProblem {
   int stat_ld;
   float* colsum_part;
   int colsum_ld;
-  const CUtensorMap* peer_tm;  // device array [num_peers] (cudaMalloc'ed by gemm_build_params, freed by the owner)
+  const CUtensorMap* peer_tm;  // device array [num_peers] (gemm_build_peer_maps; owned by the caller)
   int num_peers, rows_per_owner;
   int tiles_m, tiles_n, tile_begin, num_kb;
   int ksplit, kb_per_split;
@@ -134,6 +134,10 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
 int gemm_upload_tile_lists(GemmParams* params, int num_sms, int** d_list, char* err, int errlen);
 // the host-only half of it: flat [pairs, stride] lists, -1 padded (deterministic; cached per launch shape by the engine)
 void gemm_schedule_tile_lists(const GemmParams* params, int num_sms, std::vector<int>* flat, int* pairs, int* stride);
+// fp32 output tensor maps of the SAME [M, N] matrix (pitch ldd) at num_peers addresses (one per GPU), uploaded to a
+// device array the caller owns (cudaFree): the per-owner targets of the fused GEMM -> reduce-scatter epilogue.
+int gemm_build_peer_maps(void* const* peer_D, int num_peers, int M, int N, int ldd, CUtensorMap** d_out, char* err,
+                         int errlen);
 // Launch on `stream`.  `num_sms` = multiprocessor count of the current device.
 int gemm_launch(const GemmParams& params, int num_sms, cudaStream_t stream);
 // One-time (per process) kernel attribute setup; returns cudaError_t as int.

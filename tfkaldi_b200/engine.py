@@ -233,6 +233,12 @@ class Engine:
     def set_dropout_seed(self, seed):
         self._check(self.lib.tfk_set_dropout_seed(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF))
 
+    def activation(self, layer, frames):
+        """stored output of hidden layer `layer` from the last forward pass, fp32 [frames, hidden_dim] (diagnostic)"""
+        out = torch.empty((int(frames), self.hidden_dim), dtype=torch.float32, device=self.device)
+        self._check(self.lib.tfk_get_activation(self.h, int(layer), _ptr(out), int(frames), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ data parallel
     def init_comm_from_torch(self):
         """Create the engine's own NCCL communicator, exchanging the unique id over torch.distributed."""
@@ -252,6 +258,18 @@ class Engine:
         self._check(self.lib.tfk_comm_init(self.h, ident, rank, world))
         mode = os.environ.get("TFK_DP_MODE", "")
         if mode != "allreduce" and world & (world - 1) == 0:
+            # peer memory needs every rank on ONE host with P2P access between all device pairs; otherwise the
+            # NCCL transports (reduce-scatter / all-gather inside tfk_apply) stay in use
+            import socket
+
+            where = [None] * world
+            dist.all_gather_object(where, (socket.gethostname(), self.device.index))
+            same_host = len({h for h, _ in where}) == 1
+            p2p = same_host and all(d == self.device.index or torch.cuda.can_device_access_peer(self.device.index, d) for _, d in where)
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(p2p))
+            if not all(flags):
+                return
             # single-node peer memory: let the wgrad epilogues reduce-add into the owners' accumulators
             mine = (C.c_uint8 * 256)()
             self._check(self.lib.tfk_ipc_export(self.h, mine))

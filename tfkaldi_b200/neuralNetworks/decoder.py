@@ -10,7 +10,10 @@ from ..engine import Engine
 
 
 class Decoder(object):
-    def __init__(self, classifier, input_dim, max_length, *, precision="bf16", device=None, max_frames=16384):
+    def __init__(self, classifier, input_dim, max_length, *, precision="bf16x3", device=None, max_frames=16384):
+        """precision defaults to the fp32-equivalent mode: posteriors / log-likelihoods are what the 1e-3 contract
+        against the reference's fp32 TensorFlow arithmetic is stated on (decoder.py:26-27, 44); "bf16" is 3x faster
+        and measured at full size in tests/test_gpu_zfullsize.py (log-likelihood error ~1e-2 absolute)."""
         spec = classifier.engine_spec(input_dim)
         self.max_length = max_length
         self.input_dim = input_dim

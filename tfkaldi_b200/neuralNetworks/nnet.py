@@ -17,8 +17,15 @@ from .trainer import CrossEnthropyTrainer
 
 
 class Nnet(object):
-    def __init__(self, conf, input_dim, num_labels, *, precision="bf16", device=None, distributed=False):
-        """conf: ConfigParser with [nnet] and [directories] sections (nnet.py:17-78)"""
+    def __init__(self, conf, input_dim, num_labels, *, precision="bf16", device=None, distributed=False,
+                 decode_precision="bf16x3"):
+        """conf: ConfigParser with [nnet] and [directories] sections (nnet.py:17-78).
+
+        precision: numeric mode of TRAINING ("bf16": single-pass tensor-core GEMMs, the timed mode; "bf16x3": fp32-
+        equivalent).  decode_precision: numeric mode of decode(); the log-likelihoods Kaldi consumes carry the 1e-3
+        contract against the reference's fp32 arithmetic (nnet.py:280-286, decoder.py:26-27), which only the
+        fp32-equivalent mode meets, so that is the default."""
+        self.decode_precision = decode_precision
         self.conf = dict(conf.items("nnet"))
         self.conf["savedir"] = conf.get("directories", "expdir") + "/" + self.conf["name"]
         os.makedirs(self.conf["savedir"] + "/training", exist_ok=True)
@@ -129,11 +136,12 @@ class Nnet(object):
         # state prior (nnet.py:241-244)
         prior = dispenser.compute_target_count().astype(np.float32)
         prior = prior / prior.sum()
-        np.save(conf["savedir"] + "/prior.npy", prior)
+        if getattr(trainer, "rank", 0) == 0:  # data parallel: one writer
+            np.save(conf["savedir"] + "/prior.npy", prior)
 
     def decode(self, reader, writer):
         """pseudo log-likelihoods of every utterance of `reader` into `writer` (nnet.py:246-289)"""
-        decoder = Decoder(self.dnn, self.input_dim, reader.max_input_length, precision=self.precision, device=self.device)
+        decoder = Decoder(self.dnn, self.input_dim, reader.max_input_length, precision=self.decode_precision, device=self.device)
         prior = np.load(self.conf["savedir"] + "/prior.npy")
         decoder.restore(self.conf["savedir"] + "/final")
         prior_dev = torch.from_numpy(prior.astype(np.float32)).to(decoder.engine.device)

@@ -153,7 +153,13 @@ class Trainer(object, metaclass=ABCMeta):
         self.engine = Engine(spec["num_layers"], spec["input_dim"], spec["hidden_dim"], spec["output_dim"], self.max_frames,
                              nonlin=spec["nonlin"], batch_norm=spec["batch_norm"], keep_prob=spec["keep_prob"], l2_norm=spec["l2_norm"],
                              precision=precision, device=device, seed=seed)
+        self.distributed = bool(distributed)
+        self.rank, self.world = 0, 1
         if distributed:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
             self.engine.init_comm_from_torch()
         self._stager = None
         self.summarywriter = None
@@ -187,6 +193,7 @@ class Trainer(object, metaclass=ABCMeta):
                 for kind in (L.T_ADAM_M_BETA, L.T_ADAM_V_BETA):
                     self.engine.set_tensor(kind, l, np.zeros(n, np.float32))
         self.engine.set_scalar(L.S_GLOBAL_STEP, 0)
+        self.engine.set_scalar(L.S_ADAM_STEP, 0)  # beta1_power / beta2_power back to their initial values (init_op)
         self.engine.set_scalar(L.S_LR_FACT, 1.0)
 
     def _add_layer(self):
@@ -350,9 +357,38 @@ class Trainer(object, metaclass=ABCMeta):
 
     # ------------------------------------------------------------------ checkpoints
     # One .npz per reference checkpoint file, keyed by the reference's TF variable names.
+    def _barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+
+    def _writes_files(self):
+        """data parallel: every rank runs the (collective) tensor reads, rank 0 alone touches the files"""
+        return self.rank == 0
+
+    def _sync_moving_stats(self, params):
+        """Data parallel: a rank is one micro-batch of the step, and the reference updates the moving statistics once
+        per micro-batch, one after the other (trainer.py:164-168).  The ranks run side by side, so each holds the EMA of
+        its own micro-batches; the model that is written is their mean over ranks (all ranks call this)."""
+        if self.world <= 1 or not self.engine.batch_norm:
+            return params
+        import torch.distributed as dist
+
+        keys = sorted(k for k in params if k.startswith("moving_"))
+        flat = torch.from_numpy(np.concatenate([params[k].ravel() for k in keys])).to(self.engine.device)
+        dist.all_reduce(flat)
+        flat = (flat / self.world).cpu().numpy()
+        off = 0
+        for k in keys:
+            n = params[k].size
+            params[k] = flat[off:off + n].reshape(params[k].shape).astype(np.float32)
+            off += n
+        return params
+
     def _model_arrays(self):
         out = {}
-        for key, val in self.engine.dump_params().items():
+        for key, val in self._sync_moving_stats(self.engine.dump_params()).items():
             stem = key.rstrip("0123456789")
             layer = key[len(stem):]
             name = {v: k for k, v in MODEL_NAMES.items()}[stem]
@@ -380,7 +416,10 @@ class Trainer(object, metaclass=ABCMeta):
         return filename if filename.endswith(".npz") else filename + ".npz"
 
     def save_model(self, filename):
-        np.savez(self._path(filename), **self._model_arrays())
+        arrays = self._model_arrays()  # collective under data parallelism
+        if self._writes_files():
+            np.savez(self._path(filename), **arrays)
+        self._barrier()  # the file exists when any rank returns (restore_* reads it on every rank)
 
     def restore_model(self, filename):
         """this engine's .npz, or a checkpoint written by the reference's tf.train.Saver (V1 or V2 format)"""
@@ -397,10 +436,12 @@ class Trainer(object, metaclass=ABCMeta):
         """model + `train_variables` (global_step, learning_rate_fact) (trainer.py:465-475).  The Adam
         slots are written too (a superset: the reference never checkpoints them)."""
         self.save_model(filename)
-        np.savez(self._path(filename + "_trainvars"), **{
-            "train_variables/global_step": np.array(self.global_step, np.int32),
-            "train_variables/learning_rate_fact": np.array(self.engine.get_scalar(L.S_LR_FACT), np.float32)})
-        slots = {}
+        if self._writes_files():
+            np.savez(self._path(filename + "_trainvars"), **{
+                "train_variables/global_step": np.array(self.global_step, np.int32),
+                "train_variables/learning_rate_fact": np.array(self.engine.get_scalar(L.S_LR_FACT), np.float32)})
+        # Adam's step count (TF: beta1_power / beta2_power) belongs to the optimizer, not to train_variables
+        slots = {"adam_step": np.array(int(self.engine.get_scalar(L.S_ADAM_STEP)), np.int64)}
         for l in range(self.engine.num_layers + 1):
             slots["W%d/Adam" % l] = self.engine.get_tensor(L.T_ADAM_M_W, l)
             slots["W%d/Adam_1" % l] = self.engine.get_tensor(L.T_ADAM_V_W, l)
@@ -409,11 +450,14 @@ class Trainer(object, metaclass=ABCMeta):
             if self.engine.batch_norm and l < self.engine.num_layers:
                 slots["beta%d/Adam" % l] = self.engine.get_tensor(L.T_ADAM_M_BETA, l)
                 slots["beta%d/Adam_1" % l] = self.engine.get_tensor(L.T_ADAM_V_BETA, l)
-        np.savez(self._path(filename + "_optimizer"), **slots)
+        if self._writes_files():
+            np.savez(self._path(filename + "_optimizer"), **slots)
+        self._barrier()
 
     def restore_trainer(self, filename, restore_optimizer=False):
-        """model + train_variables.  As in the reference the live Adam moments are left untouched
-        (validation rollback keeps them, nnet.py:184-187) unless restore_optimizer=True."""
+        """model + train_variables.  As in the reference the live Adam moments AND Adam's step count (beta powers)
+        are left untouched (validation rollback keeps them, nnet.py:184-187; a resumed run starts from the freshly
+        initialised optimizer, nnet.py:134-140) unless restore_optimizer=True."""
         self.restore_model(filename)
         tv = read_model_file(filename + "_trainvars")
         self.engine.set_scalar(L.S_GLOBAL_STEP, int(tv["train_variables/global_step"]))
@@ -422,6 +466,9 @@ class Trainer(object, metaclass=ABCMeta):
             kinds = {"W": (L.T_ADAM_M_W, L.T_ADAM_V_W), "b": (L.T_ADAM_M_B, L.T_ADAM_V_B), "beta": (L.T_ADAM_M_BETA, L.T_ADAM_V_BETA)}
             with np.load(self._path(filename + "_optimizer")) as slots:
                 for key in slots.files:
+                    if key == "adam_step":
+                        self.engine.set_scalar(L.S_ADAM_STEP, int(slots[key]))
+                        continue
                     var, slot = key.split("/")
                     stem = var.rstrip("0123456789")
                     self.engine.set_tensor(kinds[stem][0 if slot == "Adam" else 1], int(var[len(stem):]), slots[key])

@@ -126,7 +126,11 @@ class ArkWriter(object):
         handle.write(key + _HDR.pack(b"B", b"F", b"M", b" ") + _DIM.pack(4, rows) + _DIM.pack(4, cols))
         handle.write(memoryview(utt_mat).cast("B"))
         slot[1] = pos + 15 + utt_mat.nbytes
+        # the reference reopened and closed the archive for every utterance (ark.py:201,211), so an entry was readable
+        # as soon as its scp line existed: keep that — archive bytes reach the file before the line that points at them
+        handle.flush()
         self.scp_file_write.write("%s %s:%s\n" % (utt_id, ark, pos))
+        self.scp_file_write.flush()
 
     def flush(self):
         for handle, _ in self._arks.values():
