@@ -67,15 +67,30 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        """host time stamp: samples between two marks are the ones taken during a timed region"""
+        return time.monotonic()
+
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi's start-up (NVML initialisation on every GPU of the box) perturbs running work for tens of
+        milliseconds: it must be over before anything is timed"""
+        t0 = time.monotonic()
+        while self.proc is not None and not self.lines and time.monotonic() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, regions=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
-        for line in self.lines:
+        lines = self.lines
+        if regions:  # a sample taken up to one period after a region's end still describes it
+            inside = [l for t, l in lines if any(a <= t <= b + 0.03 for a, b in regions)]
+            lines = [(0, l) for l in inside] if inside else lines
+        for _, line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -112,6 +127,18 @@ def make_trainer(c, precision, distributed, seed=1234):
     return tr
 
 
+def bench_config(args, world):
+    """the `config` object both arms print (identical for `--impl ours` and `--impl reference`)"""
+    c = CONFIGS[args.config]
+    B = c["frames"]
+    return {"workload": "C2: 440-6x2048-1936 DNN, ReLU, softmax-CE, Adam, %d frames/GPU/step" % B if args.config == "c2"
+            else "C4: 440-6x2048-3401 DNN, BN+ReLU+dropout(keep 0.5), softmax-CE, Adam, %d frames/GPU/step" % B,
+            "frames_per_gpu": B, "global_frames": B * world, "parallelism": "dp%d" % world}
+
+
+NUM_WINDOWS = 5
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -125,10 +152,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # clocks are sampled from BEFORE the warm-up (nvidia-smi's own start-up disturbs the GPUs and, on rank 0 only,
+    # the host thread: inside the timed region every other rank would wait for it in the first collective)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
     c = CONFIGS[args.config]
     B, I, O = c["frames"], c["input_dim"], c["output_dim"]
-    tr = make_trainer(c, args.precision, world > 1)
-    eng = tr.engine
     # synthetic data of the reference's shape: post-CMVN spliced frames ~ N(0,1), uniform pdf labels;
     # a pool of distinct batches, per-rank data seed, identical weights on every rank
     pool = 4
@@ -151,58 +182,107 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident throughput (`value`): inputs already in HBM
-    def step_resident(i):
-        # tfk_train_step == tfk_accumulate + tfk_apply (tests/test_gpu_parity.py checks bit-equality); the loss
-        # is copied to pinned memory asynchronously and read after the loop
-        eng.train_step(dev_x[i % pool], dev_y[i % pool], lr, want_loss=False)
+    regions = []
 
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = eng.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step_resident(i)
-    e1.record()
-    barrier()
-    ms_resident = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    launches = (eng.kernel_launches() - launches0) // args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    def measure(tr, windows, per_step_events=False):
+        """device-resident and end-to-end timing of one trainer: `windows` windows of exactly args.steps steps each,
+        every window bracketed by barrier + synchronize and timed with CUDA events on the launching stream, max over
+        ranks per window; the reported number is the MEDIAN window (all windows are printed)."""
+        eng = tr.engine
 
-    # ---------------- end to end (`e2e`): host buffers in, loss out, through the Trainer API
-    for i in range(max(3, args.warmup // 2)):
-        tr.update_packed(host_x[i % pool], host_y[i % pool])
-    barrier()
-    e0.record()
-    last_loss = None
-    tr.prefetch(host_x[0], host_y[0])
-    for i in range(args.steps):
-        # update_packed = wait for this batch's H2D, full step, loss D2H + host sync.  The NEXT batch's
-        # H2D is queued on the copy stream behind this step's kernels' inputs so it overlaps the step
-        # (north_star: "overlapped with the next batch's H2D copy").
-        nxt = (host_x[(i + 1) % pool], host_y[(i + 1) % pool]) if i + 1 < args.steps else None
-        last_loss = tr.update_packed(host_x[i % pool], host_y[i % pool], prefetch=nxt)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        def step_resident(i):
+            # tfk_train_step == tfk_accumulate + tfk_apply (tests/test_gpu_parity.py checks bit-equality); the loss
+            # is copied to pinned memory asynchronously and not waited for
+            eng.train_step(dev_x[i % pool], dev_y[i % pool], lr, want_loss=False)
+
+        for i in range(args.warmup):
+            step_resident(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        res, launches = [], 0
+        for w in range(windows):
+            barrier()
+            t_a = sampler.mark()
+            launches0 = eng.kernel_launches()
+            e0.record()
+            for i in range(args.steps):
+                step_resident(i)
+            e1.record()
+            barrier()
+            regions.append((t_a, sampler.mark()))
+            res.append(max_over_ranks(e0.elapsed_time(e1)) / args.steps)
+            launches = (eng.kernel_launches() - launches0) // args.steps
+        per_step = None
+        if per_step_events:  # one more window with an event after every step: exposes a stall inside a window
+            barrier()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+            evs[0].record()
+            for i in range(args.steps):
+                step_resident(i)
+                evs[i + 1].record()
+            barrier()
+            ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+            per_step = {"min": min(ms), "median": float(np.median(ms)), "max": max(ms)}
+        # ---- end to end: host buffers in, loss out, through the Trainer API
+        for i in range(3):
+            tr.update_packed(host_x[i % pool], host_y[i % pool])
+        e2e, last_loss = [], None
+        for w in range(min(windows, 3)):
+            barrier()
+            t_a = sampler.mark()
+            e0.record()
+            tr.prefetch(host_x[0], host_y[0])
+            for i in range(args.steps):
+                # update_packed = wait for this batch's H2D, full step, loss D2H + host sync.  The NEXT batch's
+                # H2D is queued on the copy stream so it overlaps the step (north_star: "overlapped with the
+                # next batch's H2D copy")
+                nxt = (host_x[(i + 1) % pool], host_y[(i + 1) % pool]) if i + 1 < args.steps else None
+                last_loss = tr.update_packed(host_x[i % pool], host_y[i % pool], prefetch=nxt)
+            e1.record()
+            barrier()
+            regions.append((t_a, sampler.mark()))
+            e2e.append(max_over_ranks(e0.elapsed_time(e1)) / args.steps)
+        return {"ms": float(np.median(res)), "windows_ms": [round(v, 4) for v in res], "launches": int(launches),
+                "e2e_ms": float(np.median(e2e)), "e2e_windows_ms": [round(v, 4) for v in e2e], "last_loss": last_loss,
+                "per_step_ms": per_step}
+
+    tr = make_trainer(c, args.precision, world > 1)
+    eng = tr.engine
+    m = measure(tr, NUM_WINDOWS, per_step_events=True)
+    ms_resident, ms_e2e, launches, last_loss = m["ms"], m["e2e_ms"], m["launches"], m["last_loss"]
+    timed_seconds = (sum(m["windows_ms"]) + sum(m["e2e_windows_ms"])) * args.steps * 1e-3
 
     # ---------------- per-kernel CUDA-event timing over the same steps (roofline numerator)
     eng.enable_timers(True)
     for i in range(args.steps):
-        step_resident(i)
+        eng.train_step(dev_x[i % pool], dev_y[i % pool], lr, want_loss=False)
     timers = eng.timers()
     eng.enable_timers(False)
+    clocks = sampler.stop(regions) if rank == 0 else None
     train_fl, fwd_fl = flops_per_frame(c)
     gemm_ms = (timers["gemm_fwd"][0] + timers["gemm_bwd"][0]) / args.steps
     gemm_launches = (timers["gemm_fwd"][1] + timers["gemm_bwd"][1]) // args.steps
     peaks = measured_peaks()
     achieved = train_fl * B / (gemm_ms * 1e-3) / 1e12
     breakdown = {k: round(v[0] / args.steps * 1e3, 1) for k, v in timers.items() if v[1]}  # us per step
+    # which measured cuBLAS figure is the fair denominator: the BURST one when the timed stretch is short and the SM
+    # clock stayed at its maximum (no power cap), the SUSTAINED one for seconds-long runs under the cap
+    sm, sm_max = (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz")
+    capped = "sw_power_cap" in ((clocks or {}).get("reasons") or []) or (sm and sm_max and sm < 0.95 * sm_max)
+    use_burst = (timed_seconds < 2.0) and not capped
+    peak = peaks["tflops_burst"] if use_burst else peaks["tflops_sustained"]
+
+    # ---------------- the fp32-equivalent (parity) mode on the same line
+    parity = None
+    if args.precision == "bf16" and not args.no_parity_mode:
+        del tr, eng
+        torch.cuda.empty_cache()
+        tr3 = make_trainer(c, "bf16x3", world > 1)
+        m3 = measure(tr3, 3)
+        parity = {"dtype": "bf16x3 (every operand as bf16 hi+lo, 3 tensor-core passes per product: fp32-equivalent; the mode every <=1e-3 parity test runs in)",
+                  "value": B * world / (m3["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": m3["ms"], "windows_ms_per_step": m3["windows_ms"],
+                  "e2e": {"value": B * world / (m3["e2e_ms"] * 1e-3), "unit": "frames/s", "ms_per_step": m3["e2e_ms"], "last_loss": m3["last_loss"]},
+                  "gpu_launches_per_step": m3["launches"]}
+        del tr3
 
     # HBM-bound kernels: algorithmic bytes / in-situ CUDA-event time (SURVEY.md 8d byte counts, adjusted to
     # what this engine actually stores: bf16 (or bf16 hi+lo) gradients / shadows)
@@ -236,19 +316,22 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-equivalent)",
             "data": "synthetic",
-            "config": {"workload": "C2: 440-6x2048-1936 DNN, ReLU, softmax-CE, Adam, %d frames/GPU/step" % B if args.config == "c2"
-                       else "C4: 440-6x2048-3401 DNN, BN+ReLU+dropout(keep 0.5), %d frames/GPU/step" % B,
-                       "frames_per_gpu": B, "global_frames": frames_total, "parallelism": "dp%d" % world, "precision": args.precision,
+            "config": bench_config(args, world),
+            "timing": {"windows": NUM_WINDOWS, "steps_per_window": args.steps, "value_is": "median window",
+                       "windows_ms_per_step": m["windows_ms"], "per_step_ms_in_an_extra_window": m["per_step_ms"],
+                       "timed_seconds": round(timed_seconds, 3),
                        "l2": "per-step working set (weights+Adam state+grads+activations ~0.9 GB) exceeds the 126 MB L2; %d rotating input batches; no explicit flush" % pool},
-            "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+            "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e, "windows_ms_per_step": m["e2e_windows_ms"],
                     "h2d_bytes_per_step": B * I * 4 + B * 4, "d2h_bytes_per_step": 16,
                     "api": "CrossEnthropyTrainer.update_packed(pinned x, pinned labels) -> loss", "last_loss": last_loss},
+            "parity_mode": parity,
             "gpu_launches": int(launches * args.steps),
             "gpu_launches_per_step": int(launches),
             "roofline": {"bound": "tensor", "kernel": "tfk_gemm2_kernel (cta_group::2 CTA pairs; fused FFLayer fwd + fused wgrad/dgrad, %d launches/step)" % gemm_launches,
-                         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
-                         "peak_source": peaks["source"] + " (cuBLAS bf16 sustained, MEASURED_PEAKS.json)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_kind": "burst" if use_burst else "sustained",
+                         "frac_of_burst_peak": achieved / peaks["tflops_burst"], "frac_of_sustained_peak": achieved / peaks["tflops_sustained"],
+                         "peak_source": peaks["source"] + " (cuBLAS bf16, MEASURED_PEAKS.json: burst for a sub-2-s timed stretch at max SM clock, else sustained)",
                          "algorithmic_flops_per_step": train_fl * B, "kernel_ms_per_step": gemm_ms, **_ncu_traffic(args, B),
                          "step_share": gemm_ms / ms_resident, "per_step_us_by_kernel_class": breakdown},
             "hbm_kernels": hbm,
@@ -358,8 +441,9 @@ def run_reference(args):
         "value": res["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": res["seconds"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 440-6x2048-1936 DNN, ReLU, softmax-CE, Adam" if args.config == "c2" else "C4", "frames_per_step": frames,
-                   "note": "reference = vrenkens/tfkaldi CrossEnthropyTrainer.update semantics restated on CPU (oracle/dnn_oracle.py); the TF-0.1x/Python-2 original cannot execute in this image"},
+        "config": bench_config(args, args.gpus),
+        "reference_note": "reference = vrenkens/tfkaldi CrossEnthropyTrainer.update semantics restated on CPU (oracle/dnn_oracle.py); the TF-0.1x/Python-2 "
+                          "original cannot execute in this image; rank 0 alone runs it, %d frames per step" % frames,
         "cpu_baseline": {"value": res["value"], "unit": "frames/s", "cores": res["cores"], "kind": "port",
                          "sample": "%d steps of %d frames each (of the %d-frame workload)" % (args.steps, frames, c["frames"])},
         "e2e": {"value": res["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -542,6 +626,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=list(CONFIGS) + ["c5", "feed"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the bf16x3 (fp32-equivalent) measurement on the same line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.config == "c5":
