@@ -245,7 +245,14 @@ class OracleDNN:
             else:
                 dz = dh
             g[f"W{l}"] = _mm(c.x.T, dz).astype(F32, copy=False)
-            g[f"b{l}"] = dz.sum(axis=0, dtype=F32)
+            if cfg.batch_norm:
+                # z = xW + b enters a batch-normalised layer only through z - mean_B(z): sum_B dz == 0 identically
+                # (sum xhat = 0).  TensorFlow's fp32 graph evaluates this zero as round-off noise, which Adam then
+                # normalises into a random walk of a parameter the training output does not depend on; that noise is
+                # not reproducible by any second implementation, so the oracle (and the engine) use the exact value.
+                g[f"b{l}"] = np.zeros(dz.shape[1], F32)
+            else:
+                g[f"b{l}"] = dz.sum(axis=0, dtype=F32)
             if l > 0:
                 da = _mm(dz, self.p[f"W{l}"].T).astype(F32, copy=False)
         return g

@@ -402,6 +402,16 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       if (!h->layers[lower].bn && !l2) {  // dz of the layer below is final here: take its column sums for free
         s[1].colsum_part = h->layers[lower].db_part;
         s[1].colsum_ld = h->layers[lower].ldn;
+      } else if (h->layers[lower].bn && !l2) {
+        // dY of the batch-norm layer below is final here: emit the partials of sum dY and sum dY*xhat (bn_bwd_finalize
+        // turns them into the two column means of the batch-norm gradient and the beta gradient).  The forward's
+        // statistics partials are idle during the backward pass and have the same [groups, npad] shape.
+        const Layer& lw = h->layers[lower];
+        s[1].colsum_part = h->bn_ps;
+        s[1].colsum2_part = h->bn_pq;
+        s[1].colsum_ld = lw.npad;
+        s[1].bn_z_hi = lw.z_hi; s[1].bn_z_lo = lw.z_lo; s[1].bn_z_ld = lw.ldn;
+        s[1].bn_mean = lw.bn_mean; s[1].bn_rstd = lw.bn_rstd;
       }
       nspec = 2;
     }
@@ -505,13 +515,23 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
     TFK_LAUNCH(h, k_l2norm_bwd(dz_hi, dz_lo, ly.u_hi, ly.u_lo, ly.l2_s, ly.ldn, B, ly.N, act_code, st));
   }
   if (ly.hidden && ly.bn) {  // d(bn output) -> d(linear output), plus dbeta
-    TimerScope ts(h, st, TFK_TIMER_BN, 3);
-    TFK_LAUNCH(h, k_bn_bwd_reduce(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
-                                  h->ws, h->bn_counters, ly.bn_sums, h->G + ly.off_beta, st));
+    TimerScope ts(h, st, TFK_TIMER_BN, 2);
+    if (fused_colsum && !h->cfg.l2_norm) {  // the dgrad epilogue of the layer above left the partial sums
+      TFK_LAUNCH(h, k_bn_bwd_finalize(h->bn_ps, h->bn_pq, (B + 31) / 32, ly.npad, ly.N, ly.ldn, ly.bn_sums,
+                                      h->G + ly.off_beta, st));
+    } else {
+      TFK_LAUNCH(h, k_bn_bwd_reduce(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
+                                    h->ws, h->bn_counters, ly.bn_sums, h->G + ly.off_beta, st));
+    }
     TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
                                  ly.bn_sums, st));
   }
-  if (!fused_colsum || !ly.hidden || ly.bn || h->cfg.l2_norm) {
+  // Bias gradient = column sums of dZ.  Under batch-norm it is identically zero: z = xW + b enters only through
+  // z - mean_B(z), so sum_B dz = rstd * (sum dy - sum dy - mean(dy xhat) * sum xhat) = 0 (layer.py:52 feeding
+  // activation.py:159).  The reference's fp32 graph evaluates that zero as round-off noise and lets Adam normalise
+  // it into a random walk of a parameter the training-mode output does not depend on; no two implementations share
+  // that noise, so the exact value is used here and in the oracle: the bias of a batch-normalised layer never moves.
+  if ((!fused_colsum || !ly.hidden || h->cfg.l2_norm) && !(ly.hidden && ly.bn)) {
     cudaStream_t cs = side ? side : st;
     if (side) {  // dZ_l is final on `st` here
       TFK_CUDA(h, cudaEventRecord(h->colsum_events[l], st));

@@ -249,6 +249,59 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       const int col = col0 + static_cast<int>(lane);
       if (col < pr.N) pr.colsum_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
     }
+    if (pr.colsum2_part != nullptr) {  // batch-norm backward: column sums of dY * xhat, xhat = (z - mean) * rstd
+      float t[32];
+      const bool full = row_ok && col0 + 32 <= pr.N;
+      const __nv_bfloat16* zp = pr.bn_z_hi + static_cast<size_t>(row) * pr.bn_z_ld + col0;
+      if (full) {
+        const uint4* z4 = reinterpret_cast<const uint4*>(zp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 zz = __ldg(z4 + j);
+          const uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            t[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
+            t[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+          }
+        }
+        if (pr.bn_z_lo != nullptr) {
+          const uint4* l4 = reinterpret_cast<const uint4*>(pr.bn_z_lo + static_cast<size_t>(row) * pr.bn_z_ld + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 zz = __ldg(l4 + j);
+            const uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              t[8 * j + 2 * k + 0] += __uint_as_float(w[k] << 16);
+              t[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = row_ok && (col0 + j) < pr.N;
+          float z = ok ? __bfloat162float(zp[j]) : 0.f;
+          if (ok && pr.bn_z_lo != nullptr)
+            z += __bfloat162float(pr.bn_z_lo[static_cast<size_t>(row) * pr.bn_z_ld + col0 + j]);
+          t[j] = z;
+        }
+      }
+      const float4* mp = reinterpret_cast<const float4*>(pr.bn_mean + col0);  // padded to a multiple of 256 floats
+      const float4* rp = reinterpret_cast<const float4*>(pr.bn_rstd + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 mu = __ldg(mp + j), rs = __ldg(rp + j);
+        t[4 * j + 0] = row_ok ? v[4 * j + 0] * ((t[4 * j + 0] - mu.x) * rs.x) : 0.f;
+        t[4 * j + 1] = row_ok ? v[4 * j + 1] * ((t[4 * j + 1] - mu.y) * rs.y) : 0.f;
+        t[4 * j + 2] = row_ok ? v[4 * j + 2] * ((t[4 * j + 2] - mu.z) * rs.z) : 0.f;
+        t[4 * j + 3] = row_ok ? v[4 * j + 3] * ((t[4 * j + 3] - mu.w) * rs.w) : 0.f;
+      }
+      const float tot = warp_transpose_reduce(t, lane);
+      const int col = col0 + static_cast<int>(lane);
+      if (col < pr.N) pr.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
+    }
 
     if constexpr (OUT == OUT_F32 || OUT == OUT_F32_REDADD) {
       if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the slab
@@ -439,16 +492,19 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
         const TileCoord tc = decode_tile(P, tile);
         const GemmProblem& pr = P.p[tc.p];
         const int m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
-        const int iters = tc.kb_count * pr.nsplit;
+        // bf16x3: a k-block is staged ONCE as two consecutive slots, (A_hi, B_hi) then (A_lo, B_lo); the MMA warp
+        // forms the three products A_hi.B_hi + A_hi.B_lo + A_lo.B_hi from them (4 operand tiles per k-block
+        // instead of the 6 that three separate (A, B) pairs would move)
+        const int loads = pr.nsplit == 3 ? 2 : 1;
+        const int iters = tc.kb_count * loads;
         int kb = tc.kb_begin, s = 0;
         for (int i = 0; i < iters; ++i) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_TILE_BYTES;
-          // bf16x3: s=0 -> (A_hi,B_hi), s=1 -> (A_hi,B_lo), s=2 -> (A_lo,B_hi)
-          const CUtensorMap* ta = &pr.tmA[s == 2 ? 1 : 0];
-          const CUtensorMap* tb = &pr.tmB[s == 1 ? 1 : 0];
+          const CUtensorMap* ta = &pr.tmA[s];
+          const CUtensorMap* tb = &pr.tmB[s];
           const int k0 = kb * BK;
           if (pr.a_mn) {
 #pragma unroll
@@ -464,7 +520,7 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
           } else {
             tma_load_2d(sb, tb, &bars->full[stage], k0, n0);
           }
-          if (++s == pr.nsplit) {
+          if (++s == loads) {
             s = 0;
             ++kb;
           }
@@ -507,8 +563,7 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
         //           advance 2 K-groups (2048 B) per UMMA_K.
         const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
         const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
-        const int iters = tc.kb_count * pr.nsplit;
-        for (int i = 0; i < iters; ++i) {
+        for (int i = 0; i < tc.kb_count; ++i) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -518,6 +573,26 @@ tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
             const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
             const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
             umma_bf16(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          if (pr.nsplit == 3) {  // + A_hi.B_lo + A_lo.B_hi with the low halves from the next slot
+            const uint32_t hi_stage = stage;
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t la = smem_base + stage * STAGE_BYTES;
+            const uint32_t lb = la + A_TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_acc, make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u),
+                        make_smem_desc_sw128(lb + k * b_kadv, b_lbo, 1024u), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_acc, make_smem_desc_sw128(la + k * a_kadv, a_lbo, 1024u),
+                        make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u), idesc, 1u);
+            umma_commit(&bars->empty[hi_stage]);
           }
           umma_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) {
@@ -632,15 +707,16 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
         const int b_atoms = half ? 1 : 2;
         // a K-major B box is always 128 rows (a half tile uses the first 64); MN-major B is loaded per 64-row atom
         const uint32_t tx = 2 * (A_TILE_BYTES + (pr.b_mn ? b_atoms * MN_ATOM_BYTES : 2 * MN_ATOM_BYTES));
-        const int iters = tc.kb_count * pr.nsplit;
+        const int loads = pr.nsplit == 3 ? 2 : 1;  // bf16x3: slots (A_hi, B_hi), (A_lo, B_lo) per k-block
+        const int iters = tc.kb_count * loads;
         int kb = tc.kb_begin, s = 0;
         for (int i = 0; i < iters; ++i) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&bars->full[stage], tx);
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
           const uint32_t sb = sa + A_TILE_BYTES;
-          const CUtensorMap* ta = &pr.tmA[s == 2 ? 1 : 0];
-          const CUtensorMap* tb = &pr.tmB[s == 1 ? 1 : 0];
+          const CUtensorMap* ta = &pr.tmA[s];
+          const CUtensorMap* tb = &pr.tmB[s];
           const int k0 = kb * BK;
           if (pr.a_mn) {
 #pragma unroll
@@ -655,7 +731,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
           } else {
             tma_load_2d_2sm(sb, tb, &bars->full[stage], k0, nb);
           }
-          if (++s == pr.nsplit) {
+          if (++s == loads) {
             s = 0;
             ++kb;
           }
@@ -682,8 +758,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
         const uint32_t idesc = make_idesc_bf16(256, (entry >> kHalfShift) ? BN / 2 : BN, pr.a_mn, pr.b_mn);
         const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
         const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
-        const int iters = tc.kb_count * pr.nsplit;
-        for (int i = 0; i < iters; ++i) {
+        for (int i = 0; i < tc.kb_count; ++i) {
           mbar_wait_cluster(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
@@ -693,6 +768,26 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
             const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
             const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
             umma_bf16_2sm(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          if (pr.nsplit == 3) {  // + A_hi.B_lo + A_lo.B_hi: the low halves of this k-block sit in the next slot
+            const uint32_t hi_stage = stage;
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1;
+            }
+            mbar_wait_cluster(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t la = smem_base + stage * STAGE2_BYTES;
+            const uint32_t lb = la + A_TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(tmem_acc, make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u),
+                            make_smem_desc_sw128(lb + k * b_kadv, b_lbo, 1024u), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(tmem_acc, make_smem_desc_sw128(la + k * a_kadv, a_lbo, 1024u),
+                            make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u), idesc, 1u);
+            umma_commit_2sm(&bars->empty[hi_stage]);
           }
           umma_commit_2sm(&bars->empty[stage]);  // frees this smem slot in BOTH CTAs
           if (++stage == STAGES2) {
@@ -909,6 +1004,16 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.stat_ld = s.stat_ld;
     p.colsum_part = s.colsum_part;
     p.colsum_ld = s.colsum_ld;
+    p.bn_z_hi = s.bn_z_hi;
+    p.bn_z_lo = s.bn_z_lo;
+    p.bn_z_ld = s.bn_z_ld;
+    p.bn_mean = s.bn_mean;
+    p.bn_rstd = s.bn_rstd;
+    p.colsum2_part = s.colsum2_part;
+    if (s.colsum2_part != nullptr && (s.colsum_part == nullptr || s.bn_z_hi == nullptr || s.bn_mean == nullptr || s.bn_rstd == nullptr)) {
+      snprintf(err, errlen, "gemm: colsum2_part needs colsum_part, bn_z_hi, bn_mean and bn_rstd");
+      return -1;
+    }
     p.peer_tm = nullptr;
     p.num_peers = 0;
     p.rows_per_owner = 0;

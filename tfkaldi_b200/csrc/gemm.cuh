@@ -77,6 +77,16 @@ struct GemmSpec {
   // gradient of the layer below falls out of the dgrad epilogue.  [ceil(M/128)*4, colsum_ld]
   float* colsum_part = nullptr;
   int colsum_ld = 0;
+  // dgrad into a batch-norm layer (reference: tf.contrib.layers.batch_norm's gradient, classifiers/activation.py:159):
+  // with colsum_part (= sum_B dY, also the beta gradient) the epilogue emits, in the same layout, the per-32-row
+  // sums of dY * xhat, xhat = (z - mean) * rstd read from the layer's stored linear output z [M, bn_z_ld] — the two
+  // column reductions the batch-norm backward needs, so no separate pass over dY and z is made for them.
+  const __nv_bfloat16* bn_z_hi = nullptr;
+  const __nv_bfloat16* bn_z_lo = nullptr;
+  int bn_z_ld = 0;
+  const float* bn_mean = nullptr;  // [>= roundup(N, 256)]
+  const float* bn_rstd = nullptr;
+  float* colsum2_part = nullptr;   // [ceil(M/128)*4, colsum_ld]
   // OUT_F32_REDADD only: fused reduce-scatter.  Output rows [o*rows_per_owner, (o+1)*rows_per_owner) are
   // reduce-added through peer_tm[o] (tensor map of the same [M, ldd] matrix on GPU o, mapped over NVLink; the
   // local matrix for this rank) instead of D_hi.  rows_per_owner must be a multiple of 32.
@@ -107,6 +117,12 @@ struct alignas(64) GemmProblem {
   int stat_ld;
   float* colsum_part;
   int colsum_ld;
+  const __nv_bfloat16* bn_z_hi;
+  const __nv_bfloat16* bn_z_lo;
+  int bn_z_ld;
+  const float* bn_mean;
+  const float* bn_rstd;
+  float* colsum2_part;
   const CUtensorMap* peer_tm;  // device array [num_peers] (gemm_build_peer_maps; owned by the caller)
   int num_peers, rows_per_owner;
   int tiles_m, tiles_n, tile_begin, num_kb;

@@ -729,6 +729,52 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat1
   if (t == 0) counters[blockIdx.x] = 0u;
 }
 
+// Finishes the two column reductions of the batch-norm backward from the per-32-row partials the dgrad epilogue wrote
+// (GemmSpec::colsum_part / colsum2_part): sums[c] = sum_B dy, sums[ld + c] = sum_B dy * xhat, g_beta[c] += sum_B dy.
+// block = 32 columns x 8 group lanes, fixed summation order.
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int groups, int pld, int N, int ld,
+                       float* __restrict__ sums, float* __restrict__ g_beta) {
+  __shared__ float sm[2][8][32];
+  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < N) {
+    int g = gl;
+    for (; g + 24 < groups; g += 32) {  // 8 independent loads in flight
+      float a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] = p1[static_cast<size_t>(g + 8 * k) * pld + c];
+        b[k] = p2[static_cast<size_t>(g + 8 * k) * pld + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s1 += a[k];
+        s2 += b[k];
+      }
+    }
+    for (; g < groups; g += 8) {
+      s1 += p1[static_cast<size_t>(g) * pld + c];
+      s2 += p2[static_cast<size_t>(g) * pld + c];
+    }
+  }
+  sm[0][gl][cl] = s1;
+  sm[1][gl][cl] = s2;
+  __syncthreads();
+  if (gl == 0 && c < N) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      t1 += sm[0][k][cl];
+      t2 += sm[1][k][cl];
+    }
+    sums[c] = t1;
+    sums[ld + c] = t2;
+    g_beta[c] += t1;
+  }
+}
+
 // dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy * xhat)), in place over dy; same tiling as bn_apply_kernel
 template <bool X3>
 __global__ void __launch_bounds__(256, 4)
@@ -1156,6 +1202,11 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
   else
     bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws, counters,
                                                       sums, g_beta);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,
+                      float* g_beta, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<(N + 31) / 32, 256, 0, st>>>(part_sum, part_dot, groups, pld, N, ld, sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,

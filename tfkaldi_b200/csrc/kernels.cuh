@@ -86,6 +86,10 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                     const float* rstd, float* ws, unsigned int* counters, float* sums, float* g_beta, cudaStream_t st);
 // dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy*xhat)), written in place over dy
+// Batch-norm backward reductions from the dgrad epilogue's per-32-row partials (part_* [groups, pld]):
+// sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat, g_beta += sum_B dy.
+int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,
+                      float* g_beta, cudaStream_t st);
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                    const float* rstd, const float* sums, cudaStream_t st);

@@ -324,7 +324,8 @@ static void run_fused_bwd(int Bsz, int Kin, int Nout, int nsplit, std::mt19937& 
   free_mat(X); free_mat(dZ); free_mat(W); cudaFree(G); cudaFree(dX_hi); cudaFree(dX_lo);
 }
 
-static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn, int out_kind, int nsplit, std::mt19937& rng) {
+static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn, int out_kind, int nsplit, std::mt19937& rng,
+                       int ksplit = 1, bool maskbits = false, int iters = 30) {
   HostMat A = a_mn ? make_mat(K, M, (M + 7) / 8 * 8, rng, true) : make_mat(M, K, (K + 7) / 8 * 8, rng, true);
   HostMat B = b_mn ? make_mat(K, N, (N + 7) / 8 * 8, rng, true, 0.05f) : make_mat(N, K, (K + 7) / 8 * 8, rng, true, 0.05f);
   const bool f32out = out_kind >= OUT_F32;
@@ -335,16 +336,24 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   s.A_hi = A.d_hi; s.A_lo = A.d_lo; s.lda = A.ld; s.a_mn = a_mn;
   s.B_hi = B.d_hi; s.B_lo = B.d_lo; s.ldb = B.ld; s.b_mn = b_mn;
   s.nsplit = nsplit; s.out_kind = out_kind; s.D_hi = D; s.D_lo = Dl; s.ldd = N; s.bias = bias; s.act = f32out ? 0 : 1;
+  s.ksplit = ksplit;
+  if (out_kind == OUT_F32_REDADD) s.bias = nullptr;
+  uint32_t* bits = nullptr;
+  if (maskbits) {  // as the training forward runs it: 1 gradient-pass bit per output element
+    CK(cudaMalloc(&bits, (size_t)((N + 31) / 32 + 8) * M * 4));
+    s.mask_bits_out = bits; s.mask_bits_ld = M;
+  }
   GemmParams P; char err[256];
   if (build(&s, 1, &P, err, sizeof(err))) { printf("bench build failed %s\n", err); return; }
   for (int i = 0; i < 3; ++i) gemm_launch(P, g_sms, 0);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int it = 30;
+  const int it = iters;
   cudaEventRecord(e0);
   for (int i = 0; i < it; ++i) gemm_launch(P, g_sms, 0);
   cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= it;
+  if (bits) cudaFree(bits);
   printf("[BENCH]%s %-34s M=%d N=%d K=%d nsplit=%d: %8.1f us  %7.1f TFLOP/s (algorithmic 2MNK: %.1f)\n", g_two_cta ? "[2cta]" : "      ", name, M, N, K, nsplit,
          ms * 1e3, 2.0 * M * N * (double)K * nsplit / ms / 1e9, 2.0 * M * N * (double)K / ms / 1e9);
   free_mat(A); free_mat(B); cudaFree(D); cudaFree(Dl); cudaFree(bias);
@@ -429,6 +438,14 @@ int main(int argc, char** argv) {
   std::mt19937 rng(1234);
   const int NS = 20000;
 
+  if (mode == "l0") {  // the north-star shape alone (8192 x 440 -> 2048), CTA-pair kernel: forward as the training step runs
+    g_two_cta = 1;     // it (bias + relu + gradient-pass bits) and the split-K weight gradient; few launches, for ncu
+    const int it = argc > 2 ? atoi(argv[2]) : 30;
+    bench_case("fwd layer0 bias+relu+bits", 8192, 2048, 440, 0, 1, OUT_BF16, 1, rng, 1, true, it);
+    bench_case("wgrad layer0 MN/MN redadd ksplit 9", 440, 2048, 8192, 1, 1, OUT_F32_REDADD, 1, rng, 9, false, it);
+    bench_case("fwd hidden bias+relu+bits", 8192, 2048, 2048, 0, 1, OUT_BF16, 1, rng, 1, true, it);
+    return 0;
+  }
   for (g_two_cta = (argc > 2 ? atoi(argv[2]) : 0); g_two_cta <= (argc > 3 ? atoi(argv[3]) : 1); ++g_two_cta) {
   if (mode != "bench") {
     std::vector<Case> cases = {
