@@ -145,6 +145,12 @@ int tfk_accumulate_raw(tfk_handle* h, const float* raw, const int32_t* utt_offse
                        const int32_t* labels, int R, int feat_dim, int context, void* stream);
 int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
                            int R, int feat_dim, int context, const float* prior, float* out, void* stream);
+/* The same for rows [row_begin, row_begin + rows) of the packed utterances only (out: fp32 [rows, O]); the splice
+ * still reads its context across the range borders from `raw`.  Lets Nnet.decode (nnet.py:267-289) pipeline a long
+ * utterance tile by tile: device->host copy and archive write of one tile while the next one is computed. */
+int tfk_forward_loglik_raw_rows(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                                int row_begin, int rows, int feat_dim, int context, const float* prior, float* out,
+                                void* stream);
 
 /* == `run([average_loss, apply_gradients_op])` + init_grads/init_loss/init_num_frames
  * (trainer.py:174-184, 337-352): [allreduce over ranks] -> grads / num_frames -> clip[-1,1] -> Adam

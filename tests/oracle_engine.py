@@ -124,7 +124,16 @@ class OracleEngine(object):
         return torch.from_numpy(self.orc.posteriors(_np(x)))
 
     def loglik(self, x, prior, out=None):
-        return torch.from_numpy(self.orc.loglik(_np(x), _np(prior)))
+        res = torch.from_numpy(self.orc.loglik(_np(x), _np(prior)))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def loglik_raw_rows(self, raw, utt_offsets, cmvn, feat_dim, context, prior, row_begin, rows, out):
+        x = self._spliced(raw, utt_offsets, cmvn, feat_dim, context)[row_begin:row_begin + rows]
+        out.copy_(torch.from_numpy(self.orc.loglik(x, _np(prior))))
+        return out
 
     def halve_lr(self):
         self.calls.append("halve_lr")
@@ -166,3 +175,21 @@ class HostStager(object):
 
     def release(self, k):
         pass
+
+
+class HostLane(object):
+    """tfkaldi_b200.neuralNetworks.decoder._Lane without a device: plain host tensors, synchronous copies"""
+
+    def __init__(self, device, tile, cols, slots):
+        self.dev_out = [torch.empty((tile, cols), dtype=torch.float32) for _ in range(2)]
+        self.pinned = [torch.empty((tile, cols), dtype=torch.float32) for _ in range(slots)]
+
+    def before_compute(self, k):
+        pass
+
+    def to_host(self, k, p, n):
+        self.pinned[p][:n].copy_(self.dev_out[k][:n])
+        return lambda: None
+
+    def upload(self, array, dtype):
+        return torch.from_numpy(np.ascontiguousarray(array, dtype=dtype))

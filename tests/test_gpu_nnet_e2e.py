@@ -165,3 +165,50 @@ def test_tensorflow_checkpoints_through_the_trainer_and_decoder(cuda_device, tmp
     assert all(np.array_equal(got[k], v) for k, v in want.items())
     with pytest.raises(FileNotFoundError):
         fresh.restore_model(str(tmp_path / "nothing_here"))
+
+
+def test_streaming_decode_tiles_and_bytes(cuda_device, tmp_path):
+    """decoder.LoglikStreamer (what Nnet.decode runs): utterances longer than the tile, so every utterance crosses
+    several device tiles, pinned slots are recycled under back-pressure (2 slots, 3 writer threads) and utterances
+    overlap.  The archive must hold exactly what one whole-utterance tfk_forward_loglik_raw call returns, in the
+    reference's byte layout (ark.py:204-210), indexed in utterance order."""
+    import torch
+
+    from oracle.dnn_oracle import OracleConfig, reference_init
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.decoder import Decoder, LoglikStreamer
+    from tfkaldi_b200.processing import ark
+    from tfkaldi_b200.processing.feeder import cmvn_coefficients
+
+    rng = np.random.default_rng(11)
+    dnn = DNN(183, 2, 256, act.TfActivation(None, act.relu), False)
+    dec = Decoder(dnn, 440, 4000, max_frames=512)
+    assert dec.engine.precision == "bf16x3"  # log-likelihoods default to the fp32-equivalent mode
+    params = reference_init(OracleConfig(2, 440, 256, 183), rng)
+    params["W2"] = (rng.standard_normal((256, 183)) / 16).astype(np.float32)
+    dec.engine.load_params(params)
+    prior = (rng.random(183) + 0.1).astype(np.float32)
+    prior /= prior.sum()
+    utts = {"utt%d" % i: (3.0 + rng.standard_normal((n, 40))).astype(np.float32) for i, n in enumerate([1500, 11, 700, 512, 513])}
+    stats = np.zeros((2, 41), np.float32)
+    stats[0, :-1], stats[0, -1], stats[1, :-1] = 3.0 * 500, 500, (9.0 + 1.3) * 500
+    writer = ark.ArkWriter(str(tmp_path / "feats.scp"), str(tmp_path / "ll.ark"))
+    stream = LoglikStreamer(dec, writer, prior, tile=512, slots=2, io_threads=3)
+    for k, m in utts.items():
+        stream.decode_raw(k, m, stats, 5)
+    stream.close()
+    writer.close()
+    out = ark.ArkReader(str(tmp_path / "feats.scp"))
+    assert out.utt_ids == list(utts)
+    raw = open(tmp_path / "ll.ark", "rb").read()
+    coef = cmvn_coefficients(stats)[None]
+    for i, (k, m) in enumerate(utts.items()):
+        want = dec.engine.loglik_raw(m, np.array([0, m.shape[0]], np.int32), coef, 40, 5, prior).cpu().numpy()
+        got = out.read_utt(k)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-5, k
+        pos = int(out.scp_data[i][1])
+        assert raw[pos - len(k):pos] == k.encode() and raw[pos:pos + 5] == b"\0BFM "
+        assert struct.unpack("<bibi", raw[pos + 5:pos + 15]) == (4, m.shape[0], 4, 183)
+    assert len(raw) == sum(len(k) + 15 + m.shape[0] * 183 * 4 for k, m in utts.items())
+    torch.cuda.synchronize()

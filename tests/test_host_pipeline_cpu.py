@@ -11,7 +11,7 @@ import pytest
 
 import tfkaldi_b200.neuralNetworks.decoder as decoder_mod
 import tfkaldi_b200.neuralNetworks.trainer as trainer_mod
-from oracle_engine import HostStager, OracleEngine  # tests/oracle_engine.py (the tests directory is on sys.path)
+from oracle_engine import HostLane, HostStager, OracleEngine  # tests/oracle_engine.py (the tests directory is on sys.path)
 from tfkaldi_b200 import _lib as L
 
 NNET = """
@@ -47,6 +47,7 @@ def host_only(monkeypatch):
     monkeypatch.setattr(trainer_mod, "Engine", OracleEngine)
     monkeypatch.setattr(trainer_mod, "_Stager", HostStager)
     monkeypatch.setattr(decoder_mod, "Engine", OracleEngine)
+    monkeypatch.setattr(decoder_mod, "_Lane", HostLane)
     OracleEngine.calls = []
     return OracleEngine
 
@@ -134,6 +135,45 @@ def test_train_then_decode_on_the_host(host_only, tmp_path, batch_norm, dropout,
         assert uid == utt and got.dtype == np.float32 and got.shape == want.shape
         finite = np.isfinite(want)
         assert np.array_equal(np.isfinite(got), finite) and np.abs(got[finite] - want[finite]).max() < 1e-5
+    # the reference's loop shape (one utterance at a time through get_utt / write_next_utt) writes the same archive,
+    # up to the fp32 round-off between host and "device" CMVN (the byte layout itself is checked in test_ark_streaming)
+    plain = tmp_path / "decode_plain"
+    plain.mkdir()
+    treader.reader.scp_position = 0
+    nnet.decode(treader, ark.ArkWriter(str(plain / "feats.scp"), str(plain / "likelihoods.ark")), streaming=False)
+    assert open(plain / "feats.scp").read().replace(str(plain), "X") == open(decodedir / "feats.scp").read().replace(str(decodedir), "X")
+    ref = ark.ArkReader(str(plain / "feats.scp"))
+    for utt in test["utts"]:
+        a, b = out.read_utt(utt), ref.read_utt(utt)
+        ok = np.isfinite(b)
+        assert a.shape == b.shape and np.abs(a[ok] - b[ok]).max() < 1e-4
+
+
+def test_ark_streaming_writes_the_same_bytes(tmp_path):
+    """ArkWriter.begin_utt / write_rows / finish_utt (the decoder's tile-by-tile output path) must produce exactly the
+    archive and index write_next_utt does (processing/ark.py:190-211 of the reference), whatever the block order"""
+    from tfkaldi_b200.processing import ark
+
+    rng = np.random.default_rng(3)
+    mats = {"uttA": rng.standard_normal((37, 11)).astype(np.float32), "b": rng.standard_normal((1, 11)).astype(np.float32),
+            "utt-c": rng.standard_normal((4100, 11)).astype(np.float32)}
+    w1 = ark.ArkWriter(str(tmp_path / "a.scp"), str(tmp_path / "a.ark"))
+    for k, m in mats.items():
+        w1.write_next_utt(k, m)
+    w1.close()
+    w2 = ark.ArkWriter(str(tmp_path / "b.scp"), str(tmp_path / "b.ark"))
+    for i, (k, m) in enumerate(mats.items()):
+        if i == 1:
+            w2.write_next_utt(k, m)  # the two styles may be mixed in one archive
+            continue
+        e = w2.begin_utt(k, *m.shape)
+        cuts = [0, 5, 6, 30, m.shape[0]] if m.shape[0] < 100 else [0, 1024, 3000, m.shape[0]]
+        for lo, hi in reversed(list(zip(cuts[:-1], cuts[1:]))):  # out of order
+            w2.write_rows(e, lo, m[lo:hi])
+        w2.finish_utt(e)
+    w2.close()
+    assert open(tmp_path / "a.ark", "rb").read() == open(tmp_path / "b.ark", "rb").read()
+    assert open(tmp_path / "a.scp").read().replace("a.ark", "b.ark") == open(tmp_path / "b.scp").read()
 
 
 def test_trainer_host_logic(host_only, tmp_path):

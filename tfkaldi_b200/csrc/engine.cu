@@ -1195,10 +1195,11 @@ int tfk_accumulate_raw(tfk_handle* h, const float* raw, const int32_t* utt_offse
   return TFK_OK;
 }
 
-int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
-                           int R, int feat_dim, int context, const float* prior, float* out, void* stream) {
+int tfk_forward_loglik_raw_rows(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                                int row_begin, int rows, int feat_dim, int context, const float* prior, float* out,
+                                void* stream) {
   if (!h || !raw || !utt_offsets || !cmvn || !out) return fail(h, TFK_EINVAL, "tfk_forward_loglik_raw: null argument");
-  if (R <= 0) return fail(h, TFK_ESHAPE, "tfk_forward_loglik_raw: R=%d must be positive", R);
+  if (rows <= 0 || row_begin < 0) return fail(h, TFK_ESHAPE, "tfk_forward_loglik_raw: rows [%d, +%d) must be a non-empty range", row_begin, rows);
   TFK_TRY(check_raw(h, "tfk_forward_loglik_raw", feat_dim, context, num_utts));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -1209,16 +1210,21 @@ int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_o
     h->launches += 1;
     log_prior = h->tmp_f32;
   }
-  for (int t0 = 0; t0 < R; t0 += maxB) {  // the splice reads across chunk borders straight from `raw`
-    const int B = (R - t0 < maxB) ? (R - t0) : maxB;
+  for (int t0 = 0; t0 < rows; t0 += maxB) {  // the splice reads across chunk borders straight from `raw`
+    const int B = (rows - t0 < maxB) ? (rows - t0) : maxB;
     Plan* plan;
     TFK_TRY(get_plan(h, B, &plan));
-    TFK_TRY(load_raw(h, raw, utt_offsets, num_utts, cmvn, feat_dim, context, t0, B, st));
+    TFK_TRY(load_raw(h, raw, utt_offsets, num_utts, cmvn, feat_dim, context, row_begin + t0, B, st));
     TFK_TRY(forward_range(h, *plan, B, false, 0, true, st));
     TimerScope ts(h, st, TFK_TIMER_DECODE_OUT);
     TFK_LAUNCH(h, k_decode_out(h->logits, h->ldo, B, O, log_prior, out + static_cast<size_t>(t0) * O, st));
   }
   return TFK_OK;
+}
+
+int tfk_forward_loglik_raw(tfk_handle* h, const float* raw, const int32_t* utt_offsets, int num_utts, const float* cmvn,
+                           int R, int feat_dim, int context, const float* prior, float* out, void* stream) {
+  return tfk_forward_loglik_raw_rows(h, raw, utt_offsets, num_utts, cmvn, 0, R, feat_dim, context, prior, out, stream);
 }
 
 int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {

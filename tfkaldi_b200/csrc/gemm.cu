@@ -110,7 +110,27 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t 
 // One 4 KB staging slab per warp (slab_a); the bf16x3 store needs two (hi, lo): there warps 2-5 do the whole
 // tile with their partner's slab as slab_b and warps 6-9 sit the tile out.
 // ------------------------------------------------------------------------------------------------
-template <int OUT>
+// Compile-time feature mask of an epilogue instantiation: a feature outside the mask is compiled out, one inside it
+// is still switched by the problem's run-time fields.  The frequent launches get lean instantiations (a few hundred
+// instructions per 32-column chunk instead of ~6000 with every branch present: the generic body does not fit the
+// instruction caches and its skipped blocks cost a fetch miss at every reconvergence point; profiles/r2_ncu_l0fwd_*),
+// everything else runs the generic one.
+enum EpiFeat : uint32_t {
+  F_BIAS = 1u << 0,        // + bias
+  F_STATS = 1u << 1,       // batch-norm statistics partials of z
+  F_RELU = 1u << 2,        // act == 1
+  F_ACT_SMOOTH = 1u << 3,  // act == 2 / 3 (sigmoid / tanh)
+  F_DROPOUT = 1u << 4,     // forward dropout (Philox)
+  F_BITS_OUT = 1u << 5,    // write the 1-bit gradient-pass mask
+  F_BITS_IN = 1u << 6,     // backward: mask from the 1-bit mask
+  F_MASK_DERIV = 1u << 7,  // backward: sigmoid / tanh slope from the stored output
+  F_MASK_RELU = 1u << 8,   // backward: mask from the stored output (> 0 or != 0)
+  F_COLSUM = 1u << 9,      // column-sum partials of the stored value
+  F_COLSUM2 = 1u << 10,    // batch-norm backward: column-sum partials of value * xhat
+  F_ALL = (1u << 11) - 1,
+};
+
+template <int OUT, uint32_t FEAT>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tmem_acc, int m0,
                                               int n0, uint32_t q, uint32_t lane, uint32_t slab_a,
                                               uint32_t slab_b, int c_begin, int c_end) {
@@ -134,7 +154,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
-    if (pr.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
+    if ((FEAT & F_BIAS) && pr.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
       const float4* bp = reinterpret_cast<const float4*>(pr.bias + col0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -145,7 +165,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         v[4 * j + 3] += b.w;
       }
     }
-    if (pr.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
+    if ((FEAT & F_STATS) && pr.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
       float s1[32], s2[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -162,17 +182,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         pr.stat_sq[o] = t2;
       }
     }
-    if (pr.act == 1) {
+    if ((FEAT & F_RELU) && pr.act == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if (pr.act == 2) {
+    } else if ((FEAT & F_ACT_SMOOTH) && pr.act == 2) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
-    } else if (pr.act == 3) {
+    } else if ((FEAT & F_ACT_SMOOTH) && pr.act == 3) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
     }
-    if (pr.drop_thr != 0u) {
+    if ((FEAT & F_DROPOUT) && pr.drop_thr != 0u) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const Philox4 rnd =
@@ -184,21 +204,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         v[4 * j + 3] = ((rnd.w >> 8) >= pr.drop_thr) ? v[4 * j + 3] * pr.keep_inv : 0.f;
       }
     }
-    if (pr.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
-      uint32_t bits = 0u;
+    if ((FEAT & F_BITS_OUT) && pr.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
+      uint32_t b4[4] = {0u, 0u, 0u, 0u};  // four independent chains (two epilogue warps per scheduler: ILP is all there is)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const bool pass = pr.mask_nonzero ? (v[j] != 0.f) : (v[j] > 0.f);
-        bits |= (pass ? 1u : 0u) << j;
+        b4[j & 3] |= (pass ? 1u : 0u) << j;
       }
-      if (row_ok) pr.mask_bits_out[static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row] = bits;
+      if (row_ok) pr.mask_bits_out[static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row] = (b4[0] | b4[1]) | (b4[2] | b4[3]);
     }
-    if (pr.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
+    if ((FEAT & F_BITS_IN) && pr.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
       const uint32_t bits = row_ok ? __ldg(pr.mask_bits_in + static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row) : 0u;
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * pr.scale : 0.f;
     }
-    if (pr.mask_src != nullptr && pr.deriv != 0) {
+    if ((FEAT & F_MASK_DERIV) && pr.mask_src != nullptr && pr.deriv != 0) {
       // backward of sigmoid / tanh (+dropout) from the stored forward output a = f(z) * dropmask / keep
       const float keep = 1.0f / pr.scale;
 #pragma unroll
@@ -213,7 +233,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         v[j] = (ok && !dropped) ? v[j] * d * pr.scale : 0.f;
       }
     } else
-    if (pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
+    if ((FEAT & F_MASK_RELU) && pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
       const __nv_bfloat16* mp = pr.mask_src + static_cast<size_t>(row) * pr.mask_ld + col0;
       if (row_ok && col0 + 32 <= pr.N) {
         const uint4* mp4 = reinterpret_cast<const uint4*>(mp);
@@ -241,7 +261,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       }
     }
 
-    if (pr.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
+    if ((FEAT & F_COLSUM) && pr.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
       float t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] = row_ok ? v[j] : 0.f;
@@ -249,7 +269,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       const int col = col0 + static_cast<int>(lane);
       if (col < pr.N) pr.colsum_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
     }
-    if (pr.colsum2_part != nullptr) {  // batch-norm backward: column sums of dY * xhat, xhat = (z - mean) * rstd
+    if ((FEAT & F_COLSUM2) && pr.colsum2_part != nullptr) {  // batch-norm backward: column sums of dY * xhat, xhat = (z - mean) * rstd
       float t[32];
       const bool full = row_ok && col0 + 32 <= pr.N;
       const __nv_bfloat16* zp = pr.bn_z_hi + static_cast<size_t>(row) * pr.bn_z_ld + col0;
@@ -400,6 +420,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
   }
 }
 
+// Which instantiation serves a problem (decided on the host, gemm_build_params): a lean one when the problem uses no
+// feature outside its mask, else the generic one.
+enum EpiVariant : int { EV_GENERIC = 0, EV_FWD_RELU_BITS, EV_FWD_STATS, EV_DGRAD_BITS_COLSUM, EV_DGRAD_BN, EV_PLAIN };
+constexpr uint32_t kFeatOf[] = {F_ALL, F_BIAS | F_RELU | F_BITS_OUT, F_BIAS | F_STATS, F_BITS_IN | F_COLSUM,
+                                F_MASK_RELU | F_COLSUM | F_COLSUM2, F_BIAS};
+
 // Tile-level dispatch shared by both kernels.  `ew` = epilogue warp index 0..7.
 __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_t tmem_acc, int m0, int n0,
                                                   uint32_t ew, uint32_t lane, uint32_t slabs, int chunks = BN / 32) {
@@ -415,7 +441,7 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_
     }
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
     if (part == 0) {
-      epilogue_tile<OUT_BF16_SPLIT>(pr, tmem_acc, m0, n0, q, lane, slab_a, slab_a + 4 * SLAB_BYTES, 0, chunks);
+      epilogue_tile<OUT_BF16_SPLIT, F_ALL>(pr, tmem_acc, m0, n0, q, lane, slab_a, slab_a + 4 * SLAB_BYTES, 0, chunks);
       if (lane == 0) tma_wait_group_read<0>();
       __syncwarp();
     }
@@ -423,15 +449,32 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_
     return;
   }
   const int c0 = static_cast<int>(part) * (chunks / 2), c1 = c0 + chunks / 2;  // chunks = 8 (256 cols) or 4 (half tile)
-  switch (pr.out_kind) {
-    case OUT_BF16:
-      epilogue_tile<OUT_BF16>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+  switch (pr.out_kind * 8 + pr.epi_variant) {
+    case OUT_BF16 * 8 + EV_FWD_RELU_BITS:
+      epilogue_tile<OUT_BF16, kFeatOf[EV_FWD_RELU_BITS]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
       break;
-    case OUT_F32:
-      epilogue_tile<OUT_F32>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+    case OUT_BF16 * 8 + EV_FWD_STATS:
+      epilogue_tile<OUT_BF16, kFeatOf[EV_FWD_STATS]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
+    case OUT_BF16 * 8 + EV_DGRAD_BITS_COLSUM:
+      epilogue_tile<OUT_BF16, kFeatOf[EV_DGRAD_BITS_COLSUM]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
+    case OUT_BF16 * 8 + EV_DGRAD_BN:
+      epilogue_tile<OUT_BF16, kFeatOf[EV_DGRAD_BN]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
+    case OUT_F32 * 8 + EV_PLAIN:
+      epilogue_tile<OUT_F32, kFeatOf[EV_PLAIN]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      break;
+    case OUT_F32_REDADD * 8 + EV_PLAIN:
+      epilogue_tile<OUT_F32_REDADD, 0u>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
       break;
     default:
-      epilogue_tile<OUT_F32_REDADD>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      if (pr.out_kind == OUT_BF16)
+        epilogue_tile<OUT_BF16, F_ALL>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      else if (pr.out_kind == OUT_F32)
+        epilogue_tile<OUT_F32, F_ALL>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      else
+        epilogue_tile<OUT_F32_REDADD, F_ALL>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
       break;
   }
 }
@@ -752,14 +795,14 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
         const TileCoord tc = decode_tile(P, entry & kTileMask);
         const GemmProblem& pr = P.p[tc.p];
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait_cluster(&bars->tmem_empty[as], aphase ^ 1);  // both CTAs' epilogues drained this stage
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);  // both CTAs' epilogues drained this stage
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * BN;
         const uint32_t idesc = make_idesc_bf16(256, (entry >> kHalfShift) ? BN / 2 : BN, pr.a_mn, pr.b_mn);
         const uint32_t a_lbo = pr.a_mn ? MN_ATOM_BYTES : 16u, b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u;
         const uint32_t a_kadv = pr.a_mn ? 2048u : 32u, b_kadv = pr.b_mn ? 2048u : 32u;
         for (int i = 0; i < tc.kb_count; ++i) {
-          mbar_wait_cluster(&bars->full[stage], phase);
+          mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
           const uint32_t sb = sa + A_TILE_BYTES;
@@ -775,7 +818,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
               stage = 0;
               phase ^= 1;
             }
-            mbar_wait_cluster(&bars->full[stage], phase);
+            mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
             const uint32_t la = smem_base + stage * STAGE2_BYTES;
             const uint32_t lb = la + A_TILE_BYTES;
@@ -809,7 +852,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
       const GemmProblem& pr = P.p[tc.p];
       const int half = entry >> kHalfShift;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      mbar_wait_cluster(&bars->tmem_full[as], aphase);
+      mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN + (half == 2 ? 128 : 0);
       if (m0 < pr.M)  // a ragged last pair-tile may leave the peer CTA without rows (CTA-uniform)
@@ -1025,6 +1068,34 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
       p.peer_tm = s.peer_tm;
       p.num_peers = s.num_peers;
       p.rows_per_owner = s.rows_per_owner;
+    }
+    {
+      // features this problem uses -> the leanest epilogue instantiation whose mask covers them
+      uint32_t used = 0;
+      if (s.bias) used |= F_BIAS;
+      if (s.stat_sum) used |= F_STATS;
+      if (s.act == 1) used |= F_RELU;
+      if (s.act >= 2) used |= F_ACT_SMOOTH;
+      if (s.keep < 1.0f) used |= F_DROPOUT;
+      if (s.mask_bits_out) used |= F_BITS_OUT;
+      if (s.mask_bits_in) used |= F_BITS_IN;
+      if (s.mask_src && s.deriv != 0) used |= F_MASK_DERIV;
+      if (s.mask_src && s.deriv == 0) used |= F_MASK_RELU;
+      if (s.colsum_part) used |= F_COLSUM;
+      if (s.colsum2_part) used |= F_COLSUM2;
+      p.epi_variant = EV_GENERIC;
+      static const char* force_generic = getenv("TFK_GEMM_GENERIC_EPILOGUE");  // tests: every launch through the generic body
+      if (!(force_generic && force_generic[0] == '1')) {
+        const int candidates[] = {EV_PLAIN, EV_FWD_RELU_BITS, EV_FWD_STATS, EV_DGRAD_BITS_COLSUM, EV_DGRAD_BN};
+        for (int v : candidates) {
+          const bool out_ok = v == EV_PLAIN ? (s.out_kind == OUT_F32 || (s.out_kind == OUT_F32_REDADD && used == 0))
+                                            : s.out_kind == OUT_BF16;
+          if (out_ok && (used & ~kFeatOf[v]) == 0) {
+            p.epi_variant = v;
+            break;
+          }
+        }
+      }
     }
     p.tiles_m = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     p.tiles_n = (s.N + BN - 1) / BN;

@@ -101,6 +101,7 @@ struct alignas(64) GemmProblem {
   CUtensorMap tmD[2];
   int M, N, K;
   int a_mn, b_mn, nsplit, out_kind;
+  int epi_variant;  // which epilogue instantiation serves this problem (gemm.cu: EpiVariant)
   int act, mask_ld, mask_nonzero, deriv;
   float scale, keep_inv;
   unsigned int drop_thr;  // keep element iff (philox >> 8) >= drop_thr; 0 => no dropout

@@ -229,10 +229,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "h"(static_cast<uint16_t>(3))
       : "memory");
 }
-// arrive on the LEADER CTA's copy of `bar` (callable from either CTA of the pair)
+// arrive on the LEADER CTA's copy of `bar` (callable from either CTA of the pair).  Default semantics (.release at
+// CTA scope): what travels with this signal is "my tcgen05.ld of the accumulator have completed", ordered by
+// tcgen05.fence::before_thread_sync — no generic-proxy data.  The cluster-scope release this used to carry compiled
+// to MEMBAR.ALL.CTA + ERRBAR per arrive (12 % of the epilogue warps' stall samples, profiles/r2_ncu_l0fwd_*).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -154,6 +154,13 @@ class Engine:
                                                     raw.shape[0], int(feat_dim), int(context), _ptr(prior), _ptr(out), self._stream()))
         return out
 
+    def loglik_raw_rows(self, raw, utt_offsets, cmvn, feat_dim, context, prior, row_begin, rows, out):
+        """rows [row_begin, row_begin + rows) of loglik_raw; raw / utt_offsets / cmvn / prior / out are DEVICE tensors"""
+        self._check(self.lib.tfk_forward_loglik_raw_rows(self.h, _ptr(raw), _ptr(utt_offsets), utt_offsets.shape[0] - 1, _ptr(cmvn),
+                                                         int(row_begin), int(rows), int(feat_dim), int(context), _ptr(prior), _ptr(out),
+                                                         self._stream()))
+        return out
+
     def apply(self, lr, want_loss=True):
         if want_loss:
             out = C.c_float()

@@ -139,11 +139,31 @@ class Nnet(object):
         if getattr(trainer, "rank", 0) == 0:  # data parallel: one writer
             np.save(conf["savedir"] + "/prior.npy", prior)
 
-    def decode(self, reader, writer):
-        """pseudo log-likelihoods of every utterance of `reader` into `writer` (nnet.py:246-289)"""
+    def decode(self, reader, writer, streaming=True):
+        """pseudo log-likelihoods of every utterance of `reader` into `writer` (nnet.py:246-289).
+
+        streaming=True (default): decoder.LoglikStreamer — raw features up (CMVN + splice on the device), the network and
+        log(softmax / prior) on the device tile by tile, device->host copies and archive writes overlapped with the
+        next tile.  Same archive bytes as streaming=False, which keeps the reference's loop: one utterance at a time,
+        get_utt() (host CMVN + splice), evaluate, write_next_utt()."""
+        from .decoder import LoglikStreamer
+
         decoder = Decoder(self.dnn, self.input_dim, reader.max_input_length, precision=self.decode_precision, device=self.device)
         prior = np.load(self.conf["savedir"] + "/prior.npy")
         decoder.restore(self.conf["savedir"] + "/final")
+        if streaming and hasattr(reader, "get_raw_utt"):
+            stream = LoglikStreamer(decoder, writer, prior.astype(np.float32))
+            width = 1 + 2 * reader.context_width
+            while True:
+                utt_id, raw, stats, looped = reader.get_raw_utt()
+                if looped:
+                    break
+                if raw.shape[0] < width:
+                    raise ValueError("%s is too short to splice" % utt_id)  # the reference fails on utt_mat None too (nnet.py:277)
+                stream.decode_raw(utt_id, raw, stats, reader.context_width)
+            stream.close()
+            writer.close()
+            return
         prior_dev = torch.from_numpy(prior.astype(np.float32)).to(decoder.engine.device)
         while True:
             utt_id, utt_mat, looped = reader.get_utt()

@@ -132,13 +132,52 @@ class ArkWriter(object):
         self.scp_file_write.write("%s %s:%s\n" % (utt_id, ark, pos))
         self.scp_file_write.flush()
 
+    # ---- streaming variant of write_next_utt (same bytes): the caller fills the matrix in pieces, from any thread
+    def begin_utt(self, utt_id, rows, cols, ark_path=None):
+        """Write the key and the matrix header of a rows x cols float32 entry and reserve the space of its data.
+        Returns a handle for write_rows / finish_utt.  Used by the decoder's output pipeline: the log-likelihoods of a
+        long utterance arrive tile by tile from the GPU (774 MB for 100 000 frames x 1936 pdf-ids) and are written with
+        positional writes straight out of pinned memory while later tiles are still being computed."""
+        ark = ark_path or self.default_ark
+        slot = self._ark(ark)
+        handle = slot[0]
+        key = utt_id.encode()
+        pos = slot[1] + len(key)
+        handle.write(key + _HDR.pack(b"B", b"F", b"M", b" ") + _DIM.pack(4, rows) + _DIM.pack(4, cols))
+        handle.flush()
+        data_offset = pos + 15
+        nbytes = int(rows) * int(cols) * 4
+        slot[1] = data_offset + nbytes
+        if len(slot) < 3:  # positional writes need a descriptor WITHOUT O_APPEND (pwrite on an append handle appends)
+            slot.append(os.open(ark, os.O_WRONLY))
+        os.ftruncate(slot[2], slot[1])  # the append handle continues after the reserved region
+        return {"utt_id": utt_id, "ark": ark, "pos": pos, "fd": slot[2], "data_offset": data_offset, "rows": int(rows),
+                "cols": int(cols)}
+
+    @staticmethod
+    def write_rows(entry, first_row, block):
+        """rows [first_row, first_row + len(block)) of a begin_utt entry; block: C-contiguous float32 [n, cols].
+        Thread-safe (os.pwrite releases the GIL): several blocks of one entry may be written concurrently."""
+        view = memoryview(block).cast("B")
+        off = entry["data_offset"] + int(first_row) * entry["cols"] * 4
+        done = 0
+        while done < len(view):
+            done += os.pwrite(entry["fd"], view[done:], off + done)
+
+    def finish_utt(self, entry):
+        """all rows are written: index the entry (scp lines appear in finish order)"""
+        self.scp_file_write.write("%s %s:%s\n" % (entry["utt_id"], entry["ark"], entry["pos"]))
+        self.scp_file_write.flush()
+
     def flush(self):
-        for handle, _ in self._arks.values():
-            handle.flush()
+        for slot in self._arks.values():
+            slot[0].flush()
         self.scp_file_write.flush()
 
     def close(self):
-        for handle, _ in self._arks.values():
-            handle.close()
+        for slot in self._arks.values():
+            slot[0].close()
+            if len(slot) > 2:
+                os.close(slot[2])
         self._arks = {}
         self.scp_file_write.close()

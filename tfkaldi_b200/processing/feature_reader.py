@@ -34,6 +34,12 @@ class FeatureReader(object):
         utt_id, utt_mat, looped = self.reader.read_next_utt()
         return utt_id, apply_cmvn(utt_mat, self._cmvn_stats(self.utt2spk[utt_id])), looped
 
+    def get_raw_utt(self):
+        """(utt_id, UN-normalised unspliced features, the speaker's CMVN statistics, looped): for the decoder's
+        device-side CMVN + splice (tfk_forward_loglik_raw)"""
+        utt_id, utt_mat, looped = self.reader.read_next_utt()
+        return utt_id, utt_mat, (None if utt_id is None else self._cmvn_stats(self.utt2spk[utt_id])), looped
+
     def next_id(self):
         return self.reader.read_next_scp()
 
