@@ -2,10 +2,10 @@
 GPU's dropout masks bit-exactly.  TEST INFRASTRUCTURE ONLY.
 
 Mask semantics: tf.nn.dropout(x, keep) = x/keep * floor(keep + u), u ~ U[0,1)
-(reference: neuralNetworks/classifiers/activation.py:140-141).  We draw u = (r >> 8) * 2^-24 from the
-Philox word r and keep the element iff (r >> 8) >= ceil((1-keep) * 2^24), i.e. floor(keep+u) == 1 in
-exact integer arithmetic.  Counter = (col >> 2, row, 0, 0), key = (seed & 0xffffffff, seed >> 32),
-the 4 output words serve columns 4*(col>>2) .. +3.
+(reference: neuralNetworks/classifiers/activation.py:140-141).  One Philox call yields eight 16-bit fields f; we draw
+u = f * 2^-16 and keep the element iff f >= ceil((1-keep) * 2^16), i.e. floor(keep+u) == 1 in exact integer
+arithmetic.  Counter = (col >> 3, row, 0, 0), key = (seed & 0xffffffff, seed >> 32); output word i serves columns
+8*(col>>3) + 2i (low half) and + 2i + 1 (high half).
 """
 import math
 
@@ -38,16 +38,18 @@ def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
 
 
 def dropout_threshold(keep: float) -> int:
-    return int(math.ceil((1.0 - float(np.float32(keep))) * 16777216.0))
+    return int(math.ceil((1.0 - float(np.float32(keep))) * 65536.0))
 
 
 def dropout_keep_mask(seed: int, rows: int, cols: int, keep: float) -> np.ndarray:
     """Boolean [rows, cols]: True where the unit is kept."""
     seed &= 0xFFFFFFFFFFFFFFFF
-    groups = (cols + 3) // 4
+    groups = (cols + 7) // 8
     r = np.arange(rows, dtype=np.uint64)[:, None] + np.zeros((1, groups), dtype=np.uint64)
     g = np.arange(groups, dtype=np.uint64)[None, :] + np.zeros((rows, 1), dtype=np.uint64)
     zeros = np.zeros_like(r)
     w = philox4x32_10(g, r, zeros, zeros, seed & 0xFFFFFFFF, seed >> 32)
-    words = np.stack(w, axis=-1).reshape(rows, groups * 4)[:, :cols]
-    return (words >> np.uint32(8)) >= np.uint32(dropout_threshold(keep))
+    words = np.stack(w, axis=-1)  # [rows, groups, 4]
+    fields = np.stack([words & np.uint32(0xFFFF), words >> np.uint32(16)], axis=-1)  # [rows, groups, 4, 2]: low half first
+    fields = fields.reshape(rows, groups * 8)[:, :cols]
+    return fields >= np.uint32(dropout_threshold(keep))

@@ -23,7 +23,7 @@ def test_philox_known_answers():
 
 
 def test_dropout_mask_semantics():
-    assert dropout_threshold(0.5) == 1 << 23
+    assert dropout_threshold(0.5) == 1 << 15
     assert dropout_threshold(1.0) == 0
     m = dropout_keep_mask(42, 512, 333, 0.8)
     assert m.shape == (512, 333) and abs(m.mean() - 0.8) < 0.01

@@ -412,6 +412,9 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
         s[1].colsum_ld = lw.npad;
         s[1].bn_z_hi = lw.z_hi; s[1].bn_z_lo = lw.z_lo; s[1].bn_z_ld = lw.ldn;
         s[1].bn_mean = lw.bn_mean; s[1].bn_rstd = lw.bn_rstd;
+        // relu / linear chains recover xhat from the stored output the mask is read from anyway (no z traffic);
+        // in bf16x3 mode that output is hi + lo
+        if (!smooth && (relu || drop)) { s[1].bn_beta = h->P + lw.off_beta; s[1].mask_src_lo = h->act_lo[ai]; }
       }
       nspec = 2;
     }

@@ -153,6 +153,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    float yv[32];  // stored forward output of the layer below (live only in instantiations with F_COLSUM2)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) yv[j] = 0.f;
 
     if ((FEAT & F_BIAS) && pr.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
       const float4* bp = reinterpret_cast<const float4*>(pr.bias + col0);
@@ -194,14 +197,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     }
     if ((FEAT & F_DROPOUT) && pr.drop_thr != 0u) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {  // one Philox call per 8 columns
         const Philox4 rnd =
-            philox4x32_10(static_cast<uint32_t>(col0 >> 2) + j, static_cast<uint32_t>(row), 0u, 0u,
+            philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
                           static_cast<uint32_t>(pr.seed), static_cast<uint32_t>(pr.seed >> 32));
-        v[4 * j + 0] = ((rnd.x >> 8) >= pr.drop_thr) ? v[4 * j + 0] * pr.keep_inv : 0.f;
-        v[4 * j + 1] = ((rnd.y >> 8) >= pr.drop_thr) ? v[4 * j + 1] * pr.keep_inv : 0.f;
-        v[4 * j + 2] = ((rnd.z >> 8) >= pr.drop_thr) ? v[4 * j + 2] * pr.keep_inv : 0.f;
-        v[4 * j + 3] = ((rnd.w >> 8) >= pr.drop_thr) ? v[4 * j + 3] * pr.keep_inv : 0.f;
+        const uint32_t keep = dropout_keep_bits(rnd, pr.drop_thr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[8 * j + k] = ((keep >> k) & 1u) ? v[8 * j + k] * pr.keep_inv : 0.f;
       }
     }
     if ((FEAT & F_BITS_OUT) && pr.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
@@ -235,6 +237,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     } else
     if ((FEAT & F_MASK_RELU) && pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
       const __nv_bfloat16* mp = pr.mask_src + static_cast<size_t>(row) * pr.mask_ld + col0;
+      const bool keep_y = (FEAT & F_COLSUM2) && pr.bn_from_y;  // the batch-norm sums below want the values, not just the signs
       if (row_ok && col0 + 32 <= pr.N) {
         const uint4* mp4 = reinterpret_cast<const uint4*>(mp);
 #pragma unroll
@@ -249,14 +252,36 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
             const bool phi = (pr.mask_nonzero || (hi & 0x8000u) == 0) && (hi & 0x7FFFu) != 0;
             v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * pr.scale : 0.f;
             v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * pr.scale : 0.f;
+            if (keep_y) {
+              yv[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
+              yv[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+            }
+          }
+        }
+        if (keep_y && pr.mask_src_lo != nullptr) {  // bf16x3: the stored output is hi + lo
+          const uint4* lp4 = reinterpret_cast<const uint4*>(pr.mask_src_lo + static_cast<size_t>(row) * pr.mask_ld + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 m = __ldg(lp4 + j);
+            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              yv[8 * j + 2 * k + 0] += __uint_as_float(w[k] << 16);
+              yv[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+            }
           }
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const bool ok = row_ok && (col0 + j) < pr.N;
-          const float mv = ok ? __bfloat162float(mp[j]) : 0.f;
+          float mv = ok ? __bfloat162float(mp[j]) : 0.f;
           v[j] = (pr.mask_nonzero ? (mv != 0.f) : (mv > 0.f)) ? v[j] * pr.scale : 0.f;
+          if (keep_y) {
+            if (ok && pr.mask_src_lo != nullptr)
+              mv += __bfloat162float(pr.mask_src_lo[static_cast<size_t>(row) * pr.mask_ld + col0 + j]);
+            yv[j] = mv;
+          }
         }
       }
     }
@@ -269,7 +294,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       const int col = col0 + static_cast<int>(lane);
       if (col < pr.N) pr.colsum_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
     }
-    if ((FEAT & F_COLSUM2) && pr.colsum2_part != nullptr) {  // batch-norm backward: column sums of dY * xhat, xhat = (z - mean) * rstd
+    if ((FEAT & F_COLSUM2) && pr.colsum2_part != nullptr && pr.bn_from_y) {
+      // batch-norm backward, column sums of dY * xhat WITHOUT reading z: the layer below stored y = f(xhat + beta) * keepmask
+      // / keep with f = relu or identity, and dY (v, already masked) is zero wherever y is, so on every element that
+      // counts xhat = y * keep - beta — from the values the mask was just derived from (no extra operand traffic in a
+      // kernel whose main loop is bound by L2 -> SM delivery)
+      float t[32];
+      const float keep = 1.0f / pr.scale;
+      const float4* bp = reinterpret_cast<const float4*>(pr.bn_beta + col0);  // padded to a multiple of 256 floats
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 be = __ldg(bp + j);
+        t[4 * j + 0] = v[4 * j + 0] * (yv[4 * j + 0] * keep - be.x);
+        t[4 * j + 1] = v[4 * j + 1] * (yv[4 * j + 1] * keep - be.y);
+        t[4 * j + 2] = v[4 * j + 2] * (yv[4 * j + 2] * keep - be.z);
+        t[4 * j + 3] = v[4 * j + 3] * (yv[4 * j + 3] * keep - be.w);
+      }
+      const float tot = warp_transpose_reduce(t, lane);
+      const int col = col0 + static_cast<int>(lane);
+      if (col < pr.N) pr.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
+    } else if ((FEAT & F_COLSUM2) && pr.colsum2_part != nullptr) {  // general form: xhat = (z - mean) * rstd from the stored z
       float t[32];
       const bool full = row_ok && col0 + 32 <= pr.N;
       const __nv_bfloat16* zp = pr.bn_z_hi + static_cast<size_t>(row) * pr.bn_z_ld + col0;
@@ -1053,8 +1097,14 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.bn_mean = s.bn_mean;
     p.bn_rstd = s.bn_rstd;
     p.colsum2_part = s.colsum2_part;
-    if (s.colsum2_part != nullptr && (s.colsum_part == nullptr || s.bn_z_hi == nullptr || s.bn_mean == nullptr || s.bn_rstd == nullptr)) {
-      snprintf(err, errlen, "gemm: colsum2_part needs colsum_part, bn_z_hi, bn_mean and bn_rstd");
+    p.bn_beta = s.bn_beta;
+    p.bn_from_y = (s.colsum2_part != nullptr && s.bn_beta != nullptr && s.mask_src != nullptr && s.deriv == 0) ? 1 : 0;
+    if (s.colsum2_part != nullptr && s.colsum_part == nullptr) {
+      snprintf(err, errlen, "gemm: colsum2_part needs colsum_part");
+      return -1;
+    }
+    if (s.colsum2_part != nullptr && !p.bn_from_y && (s.bn_z_hi == nullptr || s.bn_mean == nullptr || s.bn_rstd == nullptr)) {
+      snprintf(err, errlen, "gemm: colsum2_part needs either (bn_beta, mask_src of a relu/linear chain) or (bn_z_hi, bn_mean, bn_rstd)");
       return -1;
     }
     p.peer_tm = nullptr;

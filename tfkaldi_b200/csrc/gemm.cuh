@@ -87,6 +87,9 @@ struct GemmSpec {
   const float* bn_mean = nullptr;  // [>= roundup(N, 256)]
   const float* bn_rstd = nullptr;
   float* colsum2_part = nullptr;   // [ceil(M/128)*4, colsum_ld]
+  // relu / linear chains: with bn_beta ([>= roundup(N,256)]) and mask_src (the stored y = f(xhat + beta) * keepmask / keep)
+  // xhat is recovered as y * keep - beta on every element where dY != 0, and z is not read at all
+  const float* bn_beta = nullptr;
   // OUT_F32_REDADD only: fused reduce-scatter.  Output rows [o*rows_per_owner, (o+1)*rows_per_owner) are
   // reduce-added through peer_tm[o] (tensor map of the same [M, ldd] matrix on GPU o, mapped over NVLink; the
   // local matrix for this rank) instead of D_hi.  rows_per_owner must be a multiple of 32.
@@ -124,6 +127,8 @@ struct alignas(64) GemmProblem {
   const float* bn_mean;
   const float* bn_rstd;
   float* colsum2_part;
+  const float* bn_beta;
+  int bn_from_y;
   const CUtensorMap* peer_tm;  // device array [num_peers] (gemm_build_peer_maps; owned by the caller)
   int num_peers, rows_per_owner;
   int tiles_m, tiles_n, tile_begin, num_kb;

@@ -3,6 +3,8 @@
 
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "philox.cuh"
 
@@ -200,6 +202,78 @@ softmax_ce_kernel(const float* __restrict__ logits, int ld, const int32_t* __res
     const size_t o = static_cast<size_t>(row) * ld + e;
     *reinterpret_cast<uint2*>(d_hi + o) = h;
     if (d_lo) *reinterpret_cast<uint2*>(d_lo + o) = l;
+  }
+}
+
+// One warp per row, two sweeps: (1) running max and sum of exp in ONE pass over the logits (online softmax), (2) the
+// row is read again — it was just brought into L1/L2 — to emit loss and gradient.  Nothing but a float4 lives in
+// registers between loads (~32 registers per thread against 80-174 for the row-in-registers variant above), so six to
+// eight blocks are resident per SM and enough loads are in flight to stream the logits at HBM speed.
+__global__ void __launch_bounds__(256)
+softmax_ce_stream_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels, int B,
+                         int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
+                         __nv_bfloat16* __restrict__ d_lo) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int nvec = ld >> 2;
+  const float4* zp = reinterpret_cast<const float4*>(logits + static_cast<size_t>(row) * ld);
+  float mx = -INFINITY, sum = 0.f;
+  for (int idx0 = lane; idx0 < nvec; idx0 += 128) {  // four independent 16-byte loads in flight per lane
+    float4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + 32 * u;
+      t[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (idx < nvec) {
+        t[u] = __ldg(zp + idx);
+        const int e = idx << 2;
+        if (e + 1 > O) t[u].x = -INFINITY;
+        if (e + 2 > O) t[u].y = -INFINITY;
+        if (e + 3 > O) t[u].z = -INFINITY;
+        if (e + 4 > O) t[u].w = -INFINITY;
+      }
+    }
+    float m4 = mx;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m4 = fmaxf(m4, fmaxf(fmaxf(t[u].x, t[u].y), fmaxf(t[u].z, t[u].w)));
+    if (m4 > -INFINITY) {  // (a lane whose elements so far are all padding keeps sum = 0)
+      float part = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        part += (__expf(t[u].x - m4) + __expf(t[u].y - m4)) + (__expf(t[u].z - m4) + __expf(t[u].w - m4));
+      sum = sum * __expf(mx - m4) + part;  // exp(-inf) = 0 on the first block
+      mx = m4;
+    }
+  }
+  const float gmx = warp_max(mx);
+  sum = warp_sum(mx > -INFINITY ? sum * __expf(mx - gmx) : 0.f);
+  const int label = labels[row];
+  const bool label_ok = label >= 0 && label < O;
+  if (lane == 0) row_loss[row] = label_ok ? (logf(sum) + gmx - __ldg(logits + static_cast<size_t>(row) * ld + label)) : 0.f;
+  if (d_hi == nullptr) return;
+  const float inv = 1.0f / sum;
+  for (int idx0 = lane; idx0 < nvec; idx0 += 128) {
+    float4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (idx0 + 32 * u < nvec) t[u] = __ldg(zp + idx0 + 32 * u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + 32 * u;
+      if (idx >= nvec) continue;
+      const int e = idx << 2;
+      float p[4] = {e + 0 < O ? __expf(t[u].x - gmx) * inv : 0.f, e + 1 < O ? __expf(t[u].y - gmx) * inv : 0.f,
+                    e + 2 < O ? __expf(t[u].z - gmx) * inv : 0.f, e + 3 < O ? __expf(t[u].w - gmx) * inv : 0.f};
+      // softmax - onehot; an out-of-range label has an all-zero one-hot row (see softmax_ce_kernel)
+      if (label_ok && (label >> 2) == idx) p[label & 3] -= 1.0f;
+      uint2 h, l;
+      split2(p[0], p[1], h.x, l.x);
+      split2(p[2], p[3], h.y, l.y);
+      const size_t o = static_cast<size_t>(row) * ld + e;
+      *reinterpret_cast<uint2*>(d_hi + o) = h;
+      if (d_lo) *reinterpret_cast<uint2*>(d_lo + o) = l;
+    }
   }
 }
 
@@ -559,6 +633,14 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
           lw[u][0] = l.x; lw[u][1] = l.y; lw[u][2] = l.z; lw[u][3] = l.w;
         }
       }
+    uint32_t keepbits[BN_ROWS];
+#pragma unroll
+    for (int u = 0; u < BN_ROWS; ++u) {  // one Philox call decides the eight columns of a row
+      keepbits[u] = 0xFFu;
+      if (drop_thr != 0u && r0 + u * step < B)
+        keepbits[u] = dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(c >> 3), static_cast<uint32_t>(r0 + u * step), 0u, 0u,
+                                                      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), drop_thr);
+    }
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {  // columns c + 4 jj .. c + 4 jj + 3
       float mu[4], rs[4], be[4];
@@ -572,15 +654,6 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
       for (int u = 0; u < BN_ROWS; ++u) {
         const int r = r0 + u * step;
         if (r < B) {
-          float keepf[4] = {1.f, 1.f, 1.f, 1.f};
-          if (drop_thr != 0u) {
-            const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(c >> 2) + jj, static_cast<uint32_t>(r), 0u, 0u,
-                                              static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-            keepf[0] = ((rnd.x >> 8) >= drop_thr) ? keep_inv : 0.f;
-            keepf[1] = ((rnd.y >> 8) >= drop_thr) ? keep_inv : 0.f;
-            keepf[2] = ((rnd.z >> 8) >= drop_thr) ? keep_inv : 0.f;
-            keepf[3] = ((rnd.w >> 8) >= drop_thr) ? keep_inv : 0.f;
-          }
 #pragma unroll
           for (int w = 0; w < 2; ++w) {
             const int j = 2 * jj + w;
@@ -597,7 +670,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __r
               else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
               else if (relu == 3) y = tanhf(y);
               y = (c + 4 * jj + i < N) ? y : 0.f;
-              x[e] = (drop_thr != 0u) ? ((keepf[i] != 0.f) ? y * keepf[i] : 0.f) : y;
+              x[e] = (drop_thr != 0u) ? (((keepbits[u] >> (4 * jj + i)) & 1u) ? y * keep_inv : 0.f) : y;
             }
             split2(x[0], x[1], hw[u][j], lw[u][j]);
           }
@@ -889,15 +962,10 @@ l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ u_hi, const __nv_bfloat16* _
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (c + k < N) ? (norm ? x[k] / sig : x[k]) : 0.f;
     if (drop_thr != 0u) {
+      const uint32_t keep = dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(c >> 3), static_cast<uint32_t>(row), 0u, 0u,
+                                                            static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), drop_thr);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(c >> 2) + j, static_cast<uint32_t>(row), 0u, 0u,
-                                          static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-        x[4 * j + 0] = ((rnd.x >> 8) >= drop_thr) ? x[4 * j + 0] * keep_inv : 0.f;
-        x[4 * j + 1] = ((rnd.y >> 8) >= drop_thr) ? x[4 * j + 1] * keep_inv : 0.f;
-        x[4 * j + 2] = ((rnd.z >> 8) >= drop_thr) ? x[4 * j + 2] * keep_inv : 0.f;
-        x[4 * j + 3] = ((rnd.w >> 8) >= drop_thr) ? x[4 * j + 3] * keep_inv : 0.f;
-      }
+      for (int k = 0; k < 8; ++k) x[k] = ((keep >> k) & 1u) ? x[k] * keep_inv : 0.f;
     }
     store8(y_hi, y_lo, base + c, x);
   }
@@ -1078,7 +1146,13 @@ int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int 
                  __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, cudaStream_t st) {
   if (B <= 0) return 0;
   const int grid = (B + 7) / 8;
-  if (ld <= 1024)
+  static const int variant = [] {  // TFK_SOFTMAX=regs selects the row-in-registers kernels (A/B measurements)
+    const char* e = getenv("TFK_SOFTMAX");
+    return (e && strcmp(e, "regs") == 0) ? 1 : 0;
+  }();
+  if (variant == 0 && (ld & 3) == 0)
+    softmax_ce_stream_kernel<<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+  else if (ld <= 1024)
     softmax_ce_kernel<8><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
   else if (ld <= 2048)
     softmax_ce_kernel<16><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);

@@ -2,8 +2,11 @@
 // CPU oracle so both sides regenerate the SAME dropout mask from (seed, row, column).
 // Semantics mirrored: tf.nn.dropout(x, keep) = x/keep * floor(keep + u), u ~ U[0,1)
 // (reference: neuralNetworks/classifiers/activation.py:140-141).
-// We draw u = (x >> 8) * 2^-24 and keep the element iff (x >> 8) >= thr, thr = ceil((1-keep) * 2^24),
-// which is floor(keep + u) == 1 evaluated in exact integer arithmetic.
+// One Philox4x32-10 call yields 128 bits = EIGHT 16-bit draws: u = f * 2^-16 from field f, and the element is kept iff
+// f >= thr, thr = ceil((1-keep) * 2^16), which is floor(keep + u) == 1 evaluated in exact integer arithmetic.
+// Counter = (col >> 3, row, 0, 0), key = (seed lo, seed hi); output word i serves columns 8*(col>>3) + 2i (low half)
+// and + 2i + 1 (high half).  (Eight decisions per call instead of four halves the integer work of the dropout passes,
+// which were ALU-bound on it: profiles/r2b_ncu_full_summary_c4_small_kernels.txt.)
 #pragma once
 #include <cstdint>
 
@@ -35,12 +38,26 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
-// keep-threshold on the top 24 bits
+// keep-threshold on a 16-bit field
 inline uint32_t dropout_threshold(double keep) {
-  double t = (1.0 - keep) * 16777216.0;
+  double t = (1.0 - keep) * 65536.0;
   uint32_t thr = static_cast<uint32_t>(t);
   if (static_cast<double>(thr) < t) ++thr;  // ceil
   return thr;
+}
+
+// the eight keep decisions of one call, bit k = column 8*(col>>3) + k
+__host__ __device__ inline uint32_t dropout_keep_bits(const Philox4& r, uint32_t thr) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 4; ++i) {
+    bits |= ((w[i] & 0xFFFFu) >= thr ? 1u : 0u) << (2 * i);
+    bits |= ((w[i] >> 16) >= thr ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
 }
 
 }  // namespace tfk

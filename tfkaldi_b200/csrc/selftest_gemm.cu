@@ -178,9 +178,8 @@ static bool run_case(const Case& c, std::mt19937& rng, int nsamples) {
     if (z_out) *z_out = v;
     if (c.relu) v = v > 0 ? v : 0;
     if (c.dropout) {
-      Philox4 r = philox4x32_10((uint32_t)(n >> 2), (uint32_t)m, 0, 0, (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
-      uint32_t x = (n & 3) == 0 ? r.x : (n & 3) == 1 ? r.y : (n & 3) == 2 ? r.z : r.w;
-      v = ((x >> 8) >= thr) ? v * 2.0 : 0.0;
+      Philox4 r = philox4x32_10((uint32_t)(n >> 3), (uint32_t)m, 0, 0, (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
+      v = ((dropout_keep_bits(r, thr) >> (n & 7)) & 1u) ? v * 2.0 : 0.0;
     }
     if (c.mask) v = Mk.h[(size_t)m * c.N + n] > 0 ? v * 2.0 : 0.0;
     if (c.out_kind == OUT_F32_REDADD) v = 2.0 * v + dinit[(size_t)m * ldd + n];

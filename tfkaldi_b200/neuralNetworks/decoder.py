@@ -90,10 +90,10 @@ class LoglikStreamer(object):
     utterance, divides by the prior and takes the log on the host, and appends the matrix to the archive, one after the
     other).  Here an utterance is cut into tiles of `tile` frames; while tile i+1 runs through the network, tile i
     travels device -> pinned host memory on a copy stream and tile i-1 is written into the archive by a pool of writer
-    threads with positional writes (ArkWriter.begin_utt / write_rows / finish_utt: the same bytes write_next_utt
+    threads through a shared mapping of the archive (ArkWriter.begin_utt / write_rows / finish_utt: the same bytes write_next_utt
     produces).  The next utterance starts while the last tiles of the previous one are still being written."""
 
-    def __init__(self, decoder, writer, prior, tile=None, slots=4, io_threads=4, lane=None):
+    def __init__(self, decoder, writer, prior, tile=None, slots=4, io_threads=8, lane=None):
         self.decoder, self.writer = decoder, writer
         eng = decoder.engine
         self.tile = int(tile or eng.max_frames)
@@ -124,7 +124,7 @@ class LoglikStreamer(object):
 
         p = self.free.get()  # back-pressure: blocks while every pinned slot is still being written
         wait = self.lane.to_host(k, p, n)
-        parts = max(1, min(self.io_threads, n // 1024))
+        parts = max(1, min(self.io_threads, n // 512))
         remaining = [parts, threading.Lock()]
         step = -(-n // parts)
         for i in range(parts):

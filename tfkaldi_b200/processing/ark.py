@@ -148,24 +148,33 @@ class ArkWriter(object):
         data_offset = pos + 15
         nbytes = int(rows) * int(cols) * 4
         slot[1] = data_offset + nbytes
-        if len(slot) < 3:  # positional writes need a descriptor WITHOUT O_APPEND (pwrite on an append handle appends)
-            slot.append(os.open(ark, os.O_WRONLY))
+        if len(slot) < 3:  # a second descriptor for mapping (the append handle cannot be mapped for writing)
+            slot.append(os.open(ark, os.O_RDWR))
         os.ftruncate(slot[2], slot[1])  # the append handle continues after the reserved region
-        return {"utt_id": utt_id, "ark": ark, "pos": pos, "fd": slot[2], "data_offset": data_offset, "rows": int(rows),
-                "cols": int(cols)}
+        # The reserved region is filled through a shared mapping: write()/pwrite() on ONE file serialise on the
+        # inode lock whatever the number of threads (~2-4 GB/s on tmpfs), page-granular copies into a mapping do not.
+        entry = {"utt_id": utt_id, "ark": ark, "pos": pos, "data_offset": data_offset, "rows": int(rows), "cols": int(cols),
+                 "map": None, "bytes": None}
+        if nbytes:
+            base = data_offset - data_offset % mmap.ALLOCATIONGRANULARITY
+            entry["map"] = mmap.mmap(slot[2], data_offset + nbytes - base, offset=base)
+            entry["bytes"] = np.frombuffer(entry["map"], dtype=np.uint8, offset=data_offset - base)
+        return entry
 
     @staticmethod
     def write_rows(entry, first_row, block):
         """rows [first_row, first_row + len(block)) of a begin_utt entry; block: C-contiguous float32 [n, cols].
-        Thread-safe (os.pwrite releases the GIL): several blocks of one entry may be written concurrently."""
-        view = memoryview(block).cast("B")
-        off = entry["data_offset"] + int(first_row) * entry["cols"] * 4
-        done = 0
-        while done < len(view):
-            done += os.pwrite(entry["fd"], view[done:], off + done)
+        Thread-safe (the copy releases the GIL): several blocks of one entry may be written concurrently."""
+        block = np.ascontiguousarray(block, dtype=np.float32)
+        lo = int(first_row) * entry["cols"] * 4
+        np.copyto(entry["bytes"][lo:lo + block.nbytes], block.reshape(-1).view(np.uint8))
 
     def finish_utt(self, entry):
         """all rows are written: index the entry (scp lines appear in finish order)"""
+        if entry["map"] is not None:
+            entry["bytes"] = None  # drop the exported buffer before closing the mapping
+            entry["map"].close()
+            entry["map"] = None
         self.scp_file_write.write("%s %s:%s\n" % (entry["utt_id"], entry["ark"], entry["pos"]))
         self.scp_file_write.flush()
 
