@@ -75,6 +75,7 @@ thread_local std::string g_create_error;
 
 struct Layer {
   int K = 0, N = 0;   // in / out dimension
+  int Kpad = 0;       // rows reserved for W in the arenas (K rounded up to 512)
   int ldk = 0;        // pitch (elements) of the bf16 input activations
   int ldn = 0;        // pitch of W rows, output activations, gradient rows: round_up(N, 8)
   int npad = 0;       // padded length of per-column vectors: round_up(N, 256)
@@ -113,7 +114,7 @@ struct tfk_handle {
   bool fused_rs = false;      // weight-gradient reduce-scatter fused into the wgrad epilogue (peer memory)
   std::vector<float*> peer_G; // [nranks] every rank's gradient arena (IPC-mapped; own pointer for self)
   std::vector<__nv_bfloat16*> peer_Sh, peer_Sl;  // every rank's bf16 operand arenas
-  int* dp_flags = nullptr;                        // [256] published step per source rank (peers write here)
+  int* dp_flags = nullptr;                        // [TFK_DP_FLAG_WORDS] published epochs [slot][source rank] (peers write here)
   int** d_peer_flags = nullptr;                   // device array [nranks-1] of the OTHER ranks' flag arrays
   bool fused_ag = false;                          // Adam stores the refreshed operands into every peer (no NCCL all-gather)
   int dp_epoch = 0;
@@ -367,7 +368,7 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
     if (h->fused_rs && ly.peer_reduce) {  // add each output slab into its owner GPU's accumulator over NVLink
       s[0].peer_tm = ly.peer_tm;
       s[0].num_peers = h->nranks;
-      s[0].rows_per_owner = ly.K / h->nranks;
+      s[0].rows_per_owner = ly.Kpad / h->nranks;
     }
     int nspec = 1;
     if (ai > 0) {
@@ -380,19 +381,27 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
       s[1].B_hi = h->Sh + ly.off_w; s[1].B_lo = opt(h->Sl, ly.off_w); s[1].ldb = ly.ldn; s[1].b_mn = 0;
       s[1].out_kind = h->x3 ? OUT_BF16_SPLIT : OUT_BF16;
       s[1].D_hi = h->dA_hi[dst]; s[1].D_lo = h->dA_lo[dst]; s[1].ldd = h->layers[lower].ldn;
+      // Where the dropout mask has to be told from a stored activation, "stored value == 0" proves a drop only if the
+      // chain cannot produce an exact 0 on a kept unit.  relu can (and its slope there is 0 anyway: nothing to tell);
+      // sigmoid cannot; identity and tanh can, on pre-activations that are exactly 0 — rare, but 8192 x 2048 draws per
+      // layer find them — so those chains re-draw the keep decisions from the layer's Philox key instead.
+      const bool redraw = drop && (h->cfg.nonlin == TFK_NONLIN_LINEAR || h->cfg.nonlin == TFK_NONLIN_TANH);
       if (l2) {  // the layer below ends in L2Norm: only its dropout is undone here, the rest in k_l2norm_bwd
         if (drop) {
           s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
           s[1].mask_nonzero = 1; s[1].scale = 1.0f / h->cfg.keep_prob;
+          s[1].bwd_drop_keep = h->cfg.keep_prob;  // (relu + L2Norm: a kept 0 has slope 0 downstream, but the re-draw is exact for every chain)
         }
       } else if (smooth) {  // sigmoid / tanh: slope from the stored forward output
         s[1].mask_src = h->act_hi[ai]; s[1].mask_src_lo = h->act_lo[ai]; s[1].mask_ld = h->layers[lower].ldn;
         s[1].deriv = h->cfg.nonlin == TFK_NONLIN_SIGMOID ? 1 : 2;
         s[1].dropout_in_chain = drop ? 1 : 0;
         s[1].scale = drop ? 1.0f / h->cfg.keep_prob : 1.0f;
+        if (redraw) s[1].bwd_drop_keep = h->cfg.keep_prob;
       } else if (relu || drop) {
         if (h->layers[lower].bn) {  // activation written by bn_apply: test the stored forward output
           s[1].mask_src = h->act_hi[ai]; s[1].mask_ld = h->layers[lower].ldn;
+          if (redraw) s[1].bwd_drop_keep = h->cfg.keep_prob;
         } else {                    // 1 bit per unit, written by the forward epilogue
           s[1].mask_bits_in = h->layers[lower].maskbits; s[1].mask_bits_ld = h->cfg.max_frames;
         }
@@ -414,7 +423,11 @@ int build_plan(tfk_handle* h, int B, Plan& plan) {
         s[1].bn_mean = lw.bn_mean; s[1].bn_rstd = lw.bn_rstd;
         // relu / linear chains recover xhat from the stored output the mask is read from anyway (no z traffic);
         // in bf16x3 mode that output is hi + lo
-        if (!smooth && (relu || drop)) { s[1].bn_beta = h->P + lw.off_beta; s[1].mask_src_lo = h->act_lo[ai]; }
+        static const bool from_y = [] {  // TFK_BN_FROM_Y=0: always read z (A/B measurements)
+          const char* e = getenv("TFK_BN_FROM_Y");
+          return !(e && e[0] == '0');
+        }();
+        if (from_y && !smooth && (relu || drop)) { s[1].bn_beta = h->P + lw.off_beta; s[1].mask_src_lo = h->act_lo[ai]; }
       }
       nspec = 2;
     }
@@ -440,6 +453,20 @@ int get_plan(tfk_handle* h, int B, Plan** out) {
     it = h->plans.emplace(key, std::move(p)).first;
   }
   *out = &it->second;
+  return TFK_OK;
+}
+
+// data parallel, no host sync requested: keep the host at most `runahead` optimizer steps ahead of the device
+int bound_runahead(tfk_handle* h, cudaStream_t st) {
+  if (!(h->comm && h->nranks > 1 && h->runahead > 0)) return TFK_OK;
+  if (h->step_events.empty()) {
+    h->step_events.resize(h->runahead);
+    for (auto& e : h->step_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaEvent_t e = h->step_events[h->steps_queued % h->runahead];
+  if (h->steps_queued >= h->runahead) TFK_CUDA(h, cudaEventSynchronize(e));  // step (k - runahead) has finished
+  TFK_CUDA(h, cudaEventRecord(e, st));
+  h->steps_queued += 1;
   return TFK_OK;
 }
 
@@ -550,7 +577,10 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
   if (side && l + 1 < L) TFK_CUDA(h, cudaStreamWaitEvent(st, h->colsum_events[l + 1], 0));
   {
     TimerScope ts(h, st, TFK_TIMER_GEMM_BWD);
-    TFK_LAUNCH(h, gemm_launch(gemm_override ? *gemm_override : plan.bwd[l], h->num_sms, st));
+    GemmParams gp = gemm_override ? *gemm_override : plan.bwd[l];
+    // a dgrad epilogue that re-draws the dropout mask of the layer below needs that layer's Philox key of THIS micro-batch
+    if (gp.nprob > 1 && gp.p[1].bwd_drop_thr != 0u) gp.p[1].seed = layer_seed(h, (l == L ? h->active : l) - 1);
+    TFK_LAUNCH(h, gemm_launch(gp, h->num_sms, st));
   }
   return TFK_OK;
 }
@@ -862,7 +892,11 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     // weight regions first (each a multiple of 1024 floats so it splits evenly over 2^k ranks), then the
     // small per-column vectors: under sharded data parallelism the first part is reduce-scattered and
     // its Adam step sharded, the second part is all-reduced and replicated
-    ly.w_count = (static_cast<size_t>(ly.K) * ly.ldn + 1023) / 1024 * 1024;
+    // Rows are padded to a multiple of 512 (layer 0: 440 -> 512; the padding rows are zero and stay zero) so that every
+    // layer's rows split over 2..16 ranks in multiples of the 32-row store slab: the fused GEMM -> reduce-scatter
+    // epilogue and the sharded update then cover ALL layers and no NCCL reduce-scatter is left on the step's tail.
+    ly.Kpad = round_up(ly.K, 512);
+    ly.w_count = static_cast<size_t>(ly.Kpad) * ly.ldn;
     ly.off_w = off; off += ly.w_count;
   }
   h->nW = off;
@@ -937,7 +971,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
   CREATE_TRY(dev_alloc(h, &h->bn_counters, 512));
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
-  CREATE_TRY(dev_alloc(h, &h->dp_flags, 256));
+  CREATE_TRY(dev_alloc(h, &h->dp_flags, TFK_DP_FLAG_WORDS));
   {
     cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->acc_host), 2 * sizeof(double));
     if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "cudaMallocHost: %s", cudaGetErrorString(e)));
@@ -1279,8 +1313,8 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
       // every rank has stored its refreshed operand slices into all peers: publish, then wait for the others
       TimerScope ts(h, st, TFK_TIMER_ALLREDUCE, 2);
       h->dp_epoch += 1;
-      TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, h->rank, h->dp_epoch, st));
-      TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, h->rank, h->dp_epoch, st));
+      TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, 0, h->rank, h->dp_epoch, st));
+      TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, 0, h->rank, h->dp_epoch, st));
     } else {
       TFK_TRY(all_gather_shadows(h, st));
     }
@@ -1291,15 +1325,8 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   if (mean_loss_host) {
     TFK_CUDA(h, cudaStreamSynchronize(st));
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);  // average_loss   trainer.py:198
-  } else if (h->comm && h->nranks > 1 && h->runahead > 0) {
-    if (h->step_events.empty()) {
-      h->step_events.resize(h->runahead);
-      for (auto& e : h->step_events) TFK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    cudaEvent_t e = h->step_events[h->steps_queued % h->runahead];
-    if (h->steps_queued >= h->runahead) TFK_CUDA(h, cudaEventSynchronize(e));  // step (k - runahead) has finished
-    TFK_CUDA(h, cudaEventRecord(e, st));
-    h->steps_queued += 1;
+  } else {
+    TFK_TRY(bound_runahead(h, st));
   }
   return TFK_OK;
 }
@@ -1325,6 +1352,25 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
                                h->x3 ? h->dzo_lo : nullptr, st));
     TFK_LAUNCH(h, k_accum_loss(h->row_loss, B, h->acc, st));  // acc = {loss_sum, frames}: Adam reads frames
   }
+  const bool dp = h->comm != nullptr && h->nranks > 1;  // (dp_overlap_ready() held: fused reduce-scatter + all-gather, all layers)
+  std::vector<__nv_bfloat16*> phi, plo;
+  if (dp) {
+    // the mean gradient divides by the GLOBAL frame count (trainer.py:174): sum {loss, frames} over the ranks now, on the
+    // communication stream, so that it overlaps the output layer's backward kernel; every update below waits for it
+    NcclApi& api = nccl();
+    TFK_CUDA(h, cudaEventRecord(h->ev_compute, st));
+    TFK_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+    {
+      TimerScope ts(h, h->comm_stream, TFK_TIMER_ALLREDUCE);
+      const int rc = api.AllReduce(h->acc, h->acc, 2, kNcclDouble, kNcclSum, h->comm, h->comm_stream);
+      if (rc) return fail(h, TFK_ENCCL, "ncclAllReduce {loss, frames} failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+    }
+    TFK_CUDA(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+    TFK_CUDA(h, cudaStreamWaitEvent(h->adam_stream, h->ev_comm, 0));
+    h->dp_epoch += 1;
+    for (int r = 0; r < h->nranks; ++r)
+      if (r != h->rank) { phi.push_back(h->peer_Sh[r]); plo.push_back(h->peer_Sl[r]); }
+  }
   h->global_step += 1;
   h->adam_step += 1;
   const double t = static_cast<double>(h->adam_step);
@@ -1334,10 +1380,27 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
   auto adam_layer = [&](int l) -> int {  // weights of layer l, after its backward kernel, on the side stream
     TFK_CUDA(h, cudaEventRecord(h->layer_events[l], st));
     TFK_CUDA(h, cudaStreamWaitEvent(h->adam_stream, h->layer_events[l], 0));
+    if (!dp) {
+      TimerScope ts(h, h->adam_stream, TFK_TIMER_ADAM);
+      const size_t off = h->layers[l].off_w, cnt = h->layers[l].w_count;
+      TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, &off, &cnt, 1, h->acc, lr_t,
+                           h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->adam_stream));
+      return TFK_OK;
+    }
+    // Data parallel.  This rank's backward kernel of layer l is done: its wgrad epilogue has reduce-added every slab into
+    // the slice owner's accumulator over NVLink.  Tell the peers, wait until all of THEIR layer-l kernels are done too —
+    // from then on this rank's slice of dW_l is the global sum and nobody reads W_l any more in this step — then update
+    // the slice and store its refreshed bf16 operands into every peer, all under the backward kernels of the layers below.
+    {
+      TimerScope ts(h, h->adam_stream, TFK_TIMER_ALLREDUCE, 2);
+      TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, 1 + l, h->rank, h->dp_epoch, h->adam_stream));
+      TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, 1 + l, h->rank, h->dp_epoch, h->adam_stream));
+    }
     TimerScope ts(h, h->adam_stream, TFK_TIMER_ADAM);
-    const size_t off = h->layers[l].off_w, cnt = h->layers[l].w_count;
+    const size_t cnt = h->layers[l].w_count / h->nranks, off = h->layers[l].off_w + cnt * h->rank;
     TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, &off, &cnt, 1, h->acc, lr_t,
-                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->adam_stream));
+                         h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->adam_stream, 1,
+                         static_cast<int>(phi.size()), phi.data(), h->x3 ? plo.data() : nullptr));
     return TFK_OK;
   };
   // bias-gradient column sums that are not produced by a GEMM epilogue (output layer; BN / L2Norm layers) go to the
@@ -1366,15 +1429,30 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
   // join the side stream (output-layer column sums, per-layer Adam launches) before the bias update
   TFK_CUDA(h, cudaEventRecord(h->layer_events[h->L + 1], h->adam_stream));
   TFK_CUDA(h, cudaStreamWaitEvent(st, h->layer_events[h->L + 1], 0));
+  if (dp) {  // the small replicated vectors (biases, betas): one NCCL all-reduce, identical sums on every rank
+    NcclApi& api = nccl();
+    TimerScope ts(h, st, TFK_TIMER_ALLREDUCE);
+    const int rc = api.AllReduce(h->G + h->nW, h->G + h->nW, h->arena_n - h->nW, kNcclFloat, kNcclSum, h->comm, st);
+    if (rc) return fail(h, TFK_ENCCL, "ncclAllReduce (biases) failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+  }
   {  // biases / betas (small), then inactive layers' weight regions (zero gradients: a no-op update, kept for
      // exact equivalence with tfk_apply, which always covers the whole arena)
     TimerScope ts(h, st, TFK_TIMER_ADAM);
     size_t off[70], cnt[70];
     int n = 0;
     off[n] = h->nW; cnt[n] = h->arena_n - h->nW; ++n;
-    for (int l = h->active; l < h->L; ++l) { off[n] = h->layers[l].off_w; cnt[n] = h->layers[l].w_count; ++n; }
+    if (!dp)
+      for (int l = h->active; l < h->L; ++l) { off[n] = h->layers[l].off_w; cnt[n] = h->layers[l].w_count; ++n; }
     TFK_LAUNCH(h, k_adam(h->P, h->G, h->M, h->V, h->Sh, h->x3 ? h->Sl : nullptr, off, cnt, n, h->acc, lr_t,
                          h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, st));
+  }
+  if (dp) {
+    // every rank has stored the refreshed operands of its slices into all peers: publish, then wait for the others —
+    // the next forward pass (and the next step's remote reduce-adds into the accumulators) start behind this
+    TimerScope ts(h, st, TFK_TIMER_ALLREDUCE, 2);
+    TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, 0, h->rank, h->dp_epoch, st));
+    TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, 0, h->rank, h->dp_epoch, st));
+    h->params_synced = false;
   }
   advance_drop_seed(h);
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1382,14 +1460,32 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
   if (mean_loss_host) {
     TFK_CUDA(h, cudaStreamSynchronize(st));
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
+  } else {
+    TFK_TRY(bound_runahead(h, st));
   }
   return TFK_OK;
+}
+
+// Data parallel: the overlapped step needs the fused transports on every layer in use (peer memory on one node,
+// TFK_DP_MODE unset); anything else takes tfk_accumulate + tfk_apply.  TFK_DP_OVERLAP=0 forces the plain sequence.
+static bool dp_overlap_ready(const tfk_handle* h) {
+  if (!(h->sharded && h->fused_rs && h->fused_ag)) return false;
+  static const bool off = [] {
+    const char* e = getenv("TFK_DP_OVERLAP");
+    return e && e[0] == '0';
+  }();
+  if (off) return false;
+  for (int l = 0; l <= h->L; ++l) {
+    if (l < h->L && l >= h->active) continue;
+    if (!h->layers[l].peer_reduce) return false;
+  }
+  return true;
 }
 
 int tfk_train_step(tfk_handle* h, const float* x, const int32_t* labels, int B, float lr, float* mean_loss_host,
                    void* stream) {
   if (!h || !x || !labels) return fail(h, TFK_EINVAL, "tfk_train_step: null argument");
-  if (h->comm != nullptr || h->pending_accumulates > 0) {  // data parallel / open accumulation: plain sequence
+  if ((h->comm != nullptr && !dp_overlap_ready(h)) || h->pending_accumulates > 0) {  // plain sequence
     TFK_TRY(tfk_accumulate(h, x, labels, B, stream));
     return tfk_apply(h, lr, mean_loss_host, stream);
   }
@@ -1407,7 +1503,7 @@ int tfk_train_step_raw(tfk_handle* h, const float* raw, const int32_t* utt_offse
                        const int32_t* labels, int R, int feat_dim, int context, float lr, float* mean_loss_host,
                        void* stream) {
   if (!h || !raw || !utt_offsets || !cmvn || !labels) return fail(h, TFK_EINVAL, "tfk_train_step_raw: null argument");
-  if (h->comm != nullptr || h->pending_accumulates > 0) {
+  if ((h->comm != nullptr && !dp_overlap_ready(h)) || h->pending_accumulates > 0) {
     TFK_TRY(tfk_accumulate_raw(h, raw, utt_offsets, num_utts, cmvn, labels, R, feat_dim, context, stream));
     return tfk_apply(h, lr, mean_loss_host, stream);
   }
@@ -1597,8 +1693,7 @@ int tfk_ipc_import(tfk_handle* h, const uint8_t* handles_host, int nranks) {
   int eligible = 0;
   for (int l = 0; l <= h->L; ++l) {
     Layer& ly = h->layers[l];
-    ly.peer_reduce = ly.K % nranks == 0 && (ly.K / nranks) % 32 == 0 &&
-                     ly.w_count == static_cast<size_t>(ly.K) * ly.ldn;
+    ly.peer_reduce = ly.Kpad % nranks == 0 && (ly.Kpad / nranks) % 32 == 0;
     eligible += ly.peer_reduce ? 1 : 0;
     if (ly.peer_reduce && !ly.peer_tm) {  // per layer, once: the maps do not depend on the frame count
       std::vector<void*> peers;

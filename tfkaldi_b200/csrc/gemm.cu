@@ -127,15 +127,101 @@ enum EpiFeat : uint32_t {
   F_MASK_RELU = 1u << 8,   // backward: mask from the stored output (> 0 or != 0)
   F_COLSUM = 1u << 9,      // column-sum partials of the stored value
   F_COLSUM2 = 1u << 10,    // batch-norm backward: column-sum partials of value * xhat
-  F_ALL = (1u << 11) - 1,
+  F_BWD_PHILOX = 1u << 11, // backward: the dropout keep bits are re-drawn (chains where a stored 0 is not proof of a drop)
+  F_ALL = (1u << 12) - 1,
+};
+
+// The problem description lives in the kernel's parameter block and is indexed by a run-time problem number: every
+// `pr.x` inside the chunk loop compiles to an indexed constant load, per element where the use is predicated.  The lean
+// instantiations read each field once per tile into a local copy (fields an instantiation does not use are dead and cost
+// nothing); the generic one, which needs every register it has, keeps reading through the reference.
+struct EpiFields {
+  int M;
+  int N;
+  int act;
+  const float* bias;
+  const float* bn_beta;
+  int bn_from_y;
+  const float* bn_mean;
+  const float* bn_rstd;
+  const __nv_bfloat16* bn_z_hi;
+  int bn_z_ld;
+  const __nv_bfloat16* bn_z_lo;
+  float* colsum2_part;
+  int colsum_ld;
+  float* colsum_part;
+  int deriv;
+  unsigned int drop_thr;
+  unsigned int bwd_drop_thr;
+  int dropout_in_chain;
+  float keep_inv;
+  const uint32_t* mask_bits_in;
+  int mask_bits_ld;
+  uint32_t* mask_bits_out;
+  int mask_ld;
+  int mask_nonzero;
+  const __nv_bfloat16* mask_src;
+  const __nv_bfloat16* mask_src_lo;
+  int num_peers;
+  const CUtensorMap* peer_tm;
+  int rows_per_owner;
+  float scale;
+  unsigned long long seed;
+  int stat_ld;
+  float* stat_sq;
+  float* stat_sum;
+  __device__ __forceinline__ explicit EpiFields(const GemmProblem& p)
+      : M(p.M),
+        N(p.N),
+        act(p.act),
+        bias(p.bias),
+        bn_beta(p.bn_beta),
+        bn_from_y(p.bn_from_y),
+        bn_mean(p.bn_mean),
+        bn_rstd(p.bn_rstd),
+        bn_z_hi(p.bn_z_hi),
+        bn_z_ld(p.bn_z_ld),
+        bn_z_lo(p.bn_z_lo),
+        colsum2_part(p.colsum2_part),
+        colsum_ld(p.colsum_ld),
+        colsum_part(p.colsum_part),
+        deriv(p.deriv),
+        drop_thr(p.drop_thr),
+        bwd_drop_thr(p.bwd_drop_thr),
+        dropout_in_chain(p.dropout_in_chain),
+        keep_inv(p.keep_inv),
+        mask_bits_in(p.mask_bits_in),
+        mask_bits_ld(p.mask_bits_ld),
+        mask_bits_out(p.mask_bits_out),
+        mask_ld(p.mask_ld),
+        mask_nonzero(p.mask_nonzero),
+        mask_src(p.mask_src),
+        mask_src_lo(p.mask_src_lo),
+        num_peers(p.num_peers),
+        peer_tm(p.peer_tm),
+        rows_per_owner(p.rows_per_owner),
+        scale(p.scale),
+        seed(p.seed),
+        stat_ld(p.stat_ld),
+        stat_sq(p.stat_sq),
+        stat_sum(p.stat_sum) {}
+};
+template <uint32_t FEAT>
+struct EpiView {
+  using type = const EpiFields;
+};
+template <>
+struct EpiView<F_ALL> {
+  using type = const GemmProblem&;
 };
 
 template <int OUT, uint32_t FEAT>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tmem_acc, int m0,
                                               int n0, uint32_t q, uint32_t lane, uint32_t slab_a,
                                               uint32_t slab_b, int c_begin, int c_end) {
+  typename EpiView<FEAT>::type e(pr);
   const int row = m0 + static_cast<int>(q * 32 + lane);
-  const bool row_ok = row < pr.M;
+  const bool row_ok = row < e.M;
   const uint32_t lane_taddr = tmem_acc + ((q * 32u) << 16);
   const uint32_t row_off = lane * 128u;
   const uint32_t sw = lane & 7u;
@@ -145,7 +231,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     const int col0 = n0 + c * 32;
     // bf16 outputs are emitted in 64-column groups (two chunks), fp32 outputs per 32-column chunk
     const int group_col0 = (OUT == OUT_BF16 || OUT == OUT_BF16_SPLIT) ? (n0 + (c & ~1) * 32) : col0;
-    if (group_col0 >= pr.N) break;  // warp-uniform
+    if (group_col0 >= e.N) break;  // warp-uniform
 
     uint32_t r[32];
     tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(c * 32), r);
@@ -157,8 +243,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
 #pragma unroll
     for (int j = 0; j < 32; ++j) yv[j] = 0.f;
 
-    if ((FEAT & F_BIAS) && pr.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
-      const float4* bp = reinterpret_cast<const float4*>(pr.bias + col0);
+    if ((FEAT & F_BIAS) && e.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
+      const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = __ldg(bp + j);
@@ -168,7 +254,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         v[4 * j + 3] += b.w;
       }
     }
-    if ((FEAT & F_STATS) && pr.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
+    if ((FEAT & F_STATS) && e.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
       float s1[32], s2[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -179,66 +265,82 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       const float t1 = warp_transpose_reduce(s1, lane);
       const float t2 = warp_transpose_reduce(s2, lane);
       const int col = col0 + static_cast<int>(lane);
-      if (col < pr.N) {
-        const size_t o = static_cast<size_t>((m0 >> 5) + q) * pr.stat_ld + col;
-        pr.stat_sum[o] = t1;
-        pr.stat_sq[o] = t2;
+      if (col < e.N) {
+        const size_t o = static_cast<size_t>((m0 >> 5) + q) * e.stat_ld + col;
+        e.stat_sum[o] = t1;
+        e.stat_sq[o] = t2;
       }
     }
-    if ((FEAT & F_RELU) && pr.act == 1) {
+    if ((FEAT & F_RELU) && e.act == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if ((FEAT & F_ACT_SMOOTH) && pr.act == 2) {
+    } else if ((FEAT & F_ACT_SMOOTH) && e.act == 2) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
-    } else if ((FEAT & F_ACT_SMOOTH) && pr.act == 3) {
+    } else if ((FEAT & F_ACT_SMOOTH) && e.act == 3) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
     }
-    if ((FEAT & F_DROPOUT) && pr.drop_thr != 0u) {
+    uint32_t keepword = 0xFFFFFFFFu;  // dropout keep decisions of this chunk's 32 columns (all ones without dropout)
+    if ((FEAT & F_DROPOUT) && e.drop_thr != 0u) {
+      keepword = 0u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // one Philox call per 8 columns
         const Philox4 rnd =
             philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
-                          static_cast<uint32_t>(pr.seed), static_cast<uint32_t>(pr.seed >> 32));
-        const uint32_t keep = dropout_keep_bits(rnd, pr.drop_thr);
+                          static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32));
+        const uint32_t keep = dropout_keep_bits(rnd, e.drop_thr);
+        keepword |= keep << (8 * j);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[8 * j + k] = ((keep >> k) & 1u) ? v[8 * j + k] * pr.keep_inv : 0.f;
+        for (int k = 0; k < 8; ++k) v[8 * j + k] = ((keep >> k) & 1u) ? v[8 * j + k] * e.keep_inv : 0.f;
       }
     }
-    if ((FEAT & F_BITS_OUT) && pr.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
-      uint32_t b4[4] = {0u, 0u, 0u, 0u};  // four independent chains (two epilogue warps per scheduler: ILP is all there is)
+    if ((FEAT & F_BITS_OUT) && e.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
+      uint32_t word;
+      if (e.mask_nonzero) {
+        // identity non-linearity: the gradient passes wherever dropout kept the unit — the keep decision itself, not
+        // "stored value != 0" (a kept pre-activation that is exactly 0 would otherwise lose its gradient)
+        word = keepword;
+      } else {
+        uint32_t b4[4] = {0u, 0u, 0u, 0u};  // four independent chains (two epilogue warps per scheduler: ILP is all there is)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const bool pass = pr.mask_nonzero ? (v[j] != 0.f) : (v[j] > 0.f);
-        b4[j & 3] |= (pass ? 1u : 0u) << j;
+        for (int j = 0; j < 32; ++j) b4[j & 3] |= (v[j] > 0.f ? 1u : 0u) << j;
+        word = (b4[0] | b4[1]) | (b4[2] | b4[3]);
       }
-      if (row_ok) pr.mask_bits_out[static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row] = (b4[0] | b4[1]) | (b4[2] | b4[3]);
+      if (row_ok) e.mask_bits_out[static_cast<size_t>(col0 >> 5) * e.mask_bits_ld + row] = word;
     }
-    if ((FEAT & F_BITS_IN) && pr.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
-      const uint32_t bits = row_ok ? __ldg(pr.mask_bits_in + static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row) : 0u;
+    if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u) {  // backward: re-draw the forward pass's keep decisions
+      keepword = 0u;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * pr.scale : 0.f;
+      for (int j = 0; j < 4; ++j)
+        keepword |= dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
+                                                    static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32)),
+                                      e.bwd_drop_thr) << (8 * j);
     }
-    if ((FEAT & F_MASK_DERIV) && pr.mask_src != nullptr && pr.deriv != 0) {
+    if ((FEAT & F_BITS_IN) && e.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
+      const uint32_t bits = row_ok ? __ldg(e.mask_bits_in + static_cast<size_t>(col0 >> 5) * e.mask_bits_ld + row) : 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * e.scale : 0.f;
+    }
+    if ((FEAT & F_MASK_DERIV) && e.mask_src != nullptr && e.deriv != 0) {
       // backward of sigmoid / tanh (+dropout) from the stored forward output a = f(z) * dropmask / keep
-      const float keep = 1.0f / pr.scale;
+      const float keep = 1.0f / e.scale;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const bool ok = row_ok && (col0 + j) < pr.N;
-        const size_t o = static_cast<size_t>(row) * pr.mask_ld + col0 + j;
-        float a = ok ? __bfloat162float(pr.mask_src[o]) : 0.f;
-        if (ok && pr.mask_src_lo != nullptr) a += __bfloat162float(pr.mask_src_lo[o]);
+        const bool ok = row_ok && (col0 + j) < e.N;
+        const size_t o = static_cast<size_t>(row) * e.mask_ld + col0 + j;
+        float a = ok ? __bfloat162float(e.mask_src[o]) : 0.f;
+        if (ok && e.mask_src_lo != nullptr) a += __bfloat162float(e.mask_src_lo[o]);
         const float y = a * keep;
-        const float d = pr.deriv == 1 ? y * (1.0f - y) : 1.0f - y * y;
-        const bool dropped = pr.dropout_in_chain && a == 0.f;
-        v[j] = (ok && !dropped) ? v[j] * d * pr.scale : 0.f;
+        const float d = e.deriv == 1 ? y * (1.0f - y) : 1.0f - y * y;
+        const bool dropped = e.dropout_in_chain && (((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u) ? ((keepword >> j) & 1u) == 0u : a == 0.f);
+        v[j] = (ok && !dropped) ? v[j] * d * e.scale : 0.f;
       }
     } else
-    if ((FEAT & F_MASK_RELU) && pr.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
-      const __nv_bfloat16* mp = pr.mask_src + static_cast<size_t>(row) * pr.mask_ld + col0;
-      const bool keep_y = (FEAT & F_COLSUM2) && pr.bn_from_y;  // the batch-norm sums below want the values, not just the signs
-      if (row_ok && col0 + 32 <= pr.N) {
+    if ((FEAT & F_MASK_RELU) && e.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
+      const __nv_bfloat16* mp = e.mask_src + static_cast<size_t>(row) * e.mask_ld + col0;
+      const bool keep_y = (FEAT & F_COLSUM2) && e.bn_from_y;  // the batch-norm sums below want the values, not just the signs
+      if (row_ok && col0 + 32 <= e.N) {
         const uint4* mp4 = reinterpret_cast<const uint4*>(mp);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -248,18 +350,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
           for (int k = 0; k < 4; ++k) {
             // bf16 > 0  <=>  sign bit clear and magnitude non-zero
             const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
-            const bool plo = (pr.mask_nonzero || (lo & 0x8000u) == 0) && (lo & 0x7FFFu) != 0;
-            const bool phi = (pr.mask_nonzero || (hi & 0x8000u) == 0) && (hi & 0x7FFFu) != 0;
-            v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * pr.scale : 0.f;
-            v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * pr.scale : 0.f;
+            bool plo = (e.mask_nonzero || (lo & 0x8000u) == 0) && (lo & 0x7FFFu) != 0;
+            bool phi = (e.mask_nonzero || (hi & 0x8000u) == 0) && (hi & 0x7FFFu) != 0;
+            if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u && e.mask_nonzero) {  // identity + dropout: the keep bit decides
+              plo = (keepword >> (8 * j + 2 * k)) & 1u;
+              phi = (keepword >> (8 * j + 2 * k + 1)) & 1u;
+            }
+            v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * e.scale : 0.f;
+            v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * e.scale : 0.f;
             if (keep_y) {
               yv[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
               yv[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
             }
           }
         }
-        if (keep_y && pr.mask_src_lo != nullptr) {  // bf16x3: the stored output is hi + lo
-          const uint4* lp4 = reinterpret_cast<const uint4*>(pr.mask_src_lo + static_cast<size_t>(row) * pr.mask_ld + col0);
+        if (keep_y && e.mask_src_lo != nullptr) {  // bf16x3: the stored output is hi + lo
+          const uint4* lp4 = reinterpret_cast<const uint4*>(e.mask_src_lo + static_cast<size_t>(row) * e.mask_ld + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 m = __ldg(lp4 + j);
@@ -274,34 +380,36 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const bool ok = row_ok && (col0 + j) < pr.N;
+          const bool ok = row_ok && (col0 + j) < e.N;
           float mv = ok ? __bfloat162float(mp[j]) : 0.f;
-          v[j] = (pr.mask_nonzero ? (mv != 0.f) : (mv > 0.f)) ? v[j] * pr.scale : 0.f;
+          bool pass = e.mask_nonzero ? (mv != 0.f) : (mv > 0.f);
+          if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u && e.mask_nonzero) pass = ok && ((keepword >> j) & 1u);
+          v[j] = pass ? v[j] * e.scale : 0.f;
           if (keep_y) {
-            if (ok && pr.mask_src_lo != nullptr)
-              mv += __bfloat162float(pr.mask_src_lo[static_cast<size_t>(row) * pr.mask_ld + col0 + j]);
+            if (ok && e.mask_src_lo != nullptr)
+              mv += __bfloat162float(e.mask_src_lo[static_cast<size_t>(row) * e.mask_ld + col0 + j]);
             yv[j] = mv;
           }
         }
       }
     }
 
-    if ((FEAT & F_COLSUM) && pr.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
+    if ((FEAT & F_COLSUM) && e.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
       float t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] = row_ok ? v[j] : 0.f;
       const float tot = warp_transpose_reduce(t, lane);
       const int col = col0 + static_cast<int>(lane);
-      if (col < pr.N) pr.colsum_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
+      if (col < e.N) e.colsum_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
     }
-    if ((FEAT & F_COLSUM2) && pr.colsum2_part != nullptr && pr.bn_from_y) {
+    if ((FEAT & F_COLSUM2) && e.colsum2_part != nullptr && e.bn_from_y) {
       // batch-norm backward, column sums of dY * xhat WITHOUT reading z: the layer below stored y = f(xhat + beta) * keepmask
       // / keep with f = relu or identity, and dY (v, already masked) is zero wherever y is, so on every element that
       // counts xhat = y * keep - beta — from the values the mask was just derived from (no extra operand traffic in a
       // kernel whose main loop is bound by L2 -> SM delivery)
       float t[32];
-      const float keep = 1.0f / pr.scale;
-      const float4* bp = reinterpret_cast<const float4*>(pr.bn_beta + col0);  // padded to a multiple of 256 floats
+      const float keep = 1.0f / e.scale;
+      const float4* bp = reinterpret_cast<const float4*>(e.bn_beta + col0);  // padded to a multiple of 256 floats
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 be = __ldg(bp + j);
@@ -312,11 +420,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       }
       const float tot = warp_transpose_reduce(t, lane);
       const int col = col0 + static_cast<int>(lane);
-      if (col < pr.N) pr.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
-    } else if ((FEAT & F_COLSUM2) && pr.colsum2_part != nullptr) {  // general form: xhat = (z - mean) * rstd from the stored z
+      if (col < e.N) e.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
+    } else if ((FEAT & F_COLSUM2) && e.colsum2_part != nullptr) {  // general form: xhat = (z - mean) * rstd from the stored z
       float t[32];
-      const bool full = row_ok && col0 + 32 <= pr.N;
-      const __nv_bfloat16* zp = pr.bn_z_hi + static_cast<size_t>(row) * pr.bn_z_ld + col0;
+      const bool full = row_ok && col0 + 32 <= e.N;
+      const __nv_bfloat16* zp = e.bn_z_hi + static_cast<size_t>(row) * e.bn_z_ld + col0;
       if (full) {
         const uint4* z4 = reinterpret_cast<const uint4*>(zp);
 #pragma unroll
@@ -329,8 +437,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
             t[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
           }
         }
-        if (pr.bn_z_lo != nullptr) {
-          const uint4* l4 = reinterpret_cast<const uint4*>(pr.bn_z_lo + static_cast<size_t>(row) * pr.bn_z_ld + col0);
+        if (e.bn_z_lo != nullptr) {
+          const uint4* l4 = reinterpret_cast<const uint4*>(e.bn_z_lo + static_cast<size_t>(row) * e.bn_z_ld + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 zz = __ldg(l4 + j);
@@ -345,15 +453,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const bool ok = row_ok && (col0 + j) < pr.N;
+          const bool ok = row_ok && (col0 + j) < e.N;
           float z = ok ? __bfloat162float(zp[j]) : 0.f;
-          if (ok && pr.bn_z_lo != nullptr)
-            z += __bfloat162float(pr.bn_z_lo[static_cast<size_t>(row) * pr.bn_z_ld + col0 + j]);
+          if (ok && e.bn_z_lo != nullptr)
+            z += __bfloat162float(e.bn_z_lo[static_cast<size_t>(row) * e.bn_z_ld + col0 + j]);
           t[j] = z;
         }
       }
-      const float4* mp = reinterpret_cast<const float4*>(pr.bn_mean + col0);  // padded to a multiple of 256 floats
-      const float4* rp = reinterpret_cast<const float4*>(pr.bn_rstd + col0);
+      const float4* mp = reinterpret_cast<const float4*>(e.bn_mean + col0);  // padded to a multiple of 256 floats
+      const float4* rp = reinterpret_cast<const float4*>(e.bn_rstd + col0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 mu = __ldg(mp + j), rs = __ldg(rp + j);
@@ -364,7 +472,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
       }
       const float tot = warp_transpose_reduce(t, lane);
       const int col = col0 + static_cast<int>(lane);
-      if (col < pr.N) pr.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * pr.colsum_ld + col] = tot;
+      if (col < e.N) e.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
     }
 
     if constexpr (OUT == OUT_F32 || OUT == OUT_F32_REDADD) {
@@ -387,10 +495,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         } else {
           // fused reduce-scatter: this 32-row slab belongs to one owner GPU; add it there over NVLink
           const CUtensorMap* tm = &pr.tmD[0];
-          if (pr.peer_tm != nullptr) {
-            int owner = (m0 + static_cast<int>(q * 32)) / pr.rows_per_owner;
-            owner = owner < pr.num_peers ? owner : pr.num_peers - 1;
-            tm = pr.peer_tm + owner;
+          if (e.peer_tm != nullptr) {
+            int owner = (m0 + static_cast<int>(q * 32)) / e.rows_per_owner;
+            owner = owner < e.num_peers ? owner : e.num_peers - 1;
+            tm = e.peer_tm + owner;
           }
           tma_reduce_add_2d(tm, src, col0, m0 + static_cast<int>(q * 32));
         }
@@ -1083,6 +1191,7 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     p.scale = s.scale;
     p.keep_inv = 1.0f / s.keep;
     p.drop_thr = (s.keep < 1.0f) ? dropout_threshold(s.keep) : 0u;
+    p.bwd_drop_thr = (s.bwd_drop_keep < 1.0f) ? dropout_threshold(s.bwd_drop_keep) : 0u;
     p.bias = s.bias;
     p.mask_src = s.mask_src;
     p.seed = s.seed;
@@ -1133,6 +1242,7 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
       if (s.mask_src && s.deriv == 0) used |= F_MASK_RELU;
       if (s.colsum_part) used |= F_COLSUM;
       if (s.colsum2_part) used |= F_COLSUM2;
+      if (s.bwd_drop_keep < 1.0f) used |= F_BWD_PHILOX;
       p.epi_variant = EV_GENERIC;
       static const char* force_generic = getenv("TFK_GEMM_GENERIC_EPILOGUE");  // tests: every launch through the generic body
       if (!(force_generic && force_generic[0] == '1')) {

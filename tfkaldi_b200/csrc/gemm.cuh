@@ -68,7 +68,11 @@ struct GemmSpec {
   int mask_bits_ld = 0;
   // forward dropout (reference: classifiers/activation.py:140-141): keep<1 => v = v/keep * floor(keep+u)
   float keep = 1.0f;
-  unsigned long long seed = 0;  // Philox key; counter = row*N + col
+  unsigned long long seed = 0;  // Philox key; counter = (col / 8, row)
+  // backward through a chain whose stored output does not prove a drop (identity or tanh before the dropout: a kept
+  // unit may hold an exact 0): < 1 makes the epilogue re-draw the forward pass's keep decisions from `seed` (the key of
+  // the layer below's forward dropout) instead of testing the stored value
+  float bwd_drop_keep = 1.0f;
   // per-(128-row tile, column) partial sums of v and v*v taken BEFORE relu/dropout (batch-norm stats)
   float* stat_sum = nullptr;  // [tiles_m, stat_ld]
   float* stat_sq = nullptr;
@@ -107,7 +111,8 @@ struct alignas(64) GemmProblem {
   int epi_variant;  // which epilogue instantiation serves this problem (gemm.cu: EpiVariant)
   int act, mask_ld, mask_nonzero, deriv;
   float scale, keep_inv;
-  unsigned int drop_thr;  // keep element iff (philox >> 8) >= drop_thr; 0 => no dropout
+  unsigned int drop_thr;  // keep element iff its 16-bit Philox field >= drop_thr; 0 => no dropout
+  unsigned int bwd_drop_thr;  // backward: re-draw the keep bits with this threshold (0 => derive the mask from stored values)
   const float* bias;
   const __nv_bfloat16* mask_src;
   const __nv_bfloat16* mask_src_lo;

@@ -473,22 +473,24 @@ adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__
   if (segs.n_bcast > 0) __threadfence_system();  // remote stores visible before the kernel is seen as done
 }
 
-// publish / wait: one flag word per source rank in every GPU's flag array (peer-mapped)
-__global__ void dp_publish_kernel(int* const* __restrict__ peer_flags, int n_peers, int me, int value) {
+// publish / wait: flag words [slot][source rank] in every GPU's flag array (peer-mapped); slot 0 = "my operand stores
+// of this step have landed", slot 1 + l = "my backward kernel of layer l has finished (its remote reduce-adds are done)"
+constexpr int kFlagStride = 16;  // ranks per slot
+__global__ void dp_publish_kernel(int* const* __restrict__ peer_flags, int n_peers, int slot, int me, int value) {
   const int r = threadIdx.x;
   if (r < n_peers) {
     __threadfence_system();
-    *(reinterpret_cast<volatile int*>(peer_flags[r]) + me) = value;
+    *(reinterpret_cast<volatile int*>(peer_flags[r]) + slot * kFlagStride + me) = value;
   }
 }
-__global__ void dp_wait_kernel(const int* __restrict__ flags, int n_ranks, int me, int value) {
+__global__ void dp_wait_kernel(const int* __restrict__ flags, int n_ranks, int slot, int me, int value) {
   const int r = threadIdx.x;
   if (r < n_ranks && r != me) {
-    const volatile int* f = flags + r;
+    const volatile int* f = flags + slot * kFlagStride + r;
     const long long t0 = clock64();
     while (*f < value) {
       if (clock64() - t0 > 6000000000LL) {
-        printf("tfk: timeout waiting for rank %d to publish step %d (have %d)\n", r, value, *f);
+        printf("tfk: timeout waiting for rank %d to publish step %d in slot %d (have %d)\n", r, value, slot, *f);
         __trap();
       }
     }
@@ -1227,12 +1229,12 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
   return static_cast<int>(cudaGetLastError());
 }
 
-int k_dp_publish(int* const* d_peer_flags, int n_peers, int me, int value, cudaStream_t st) {
-  dp_publish_kernel<<<1, 32, 0, st>>>(d_peer_flags, n_peers, me, value);
+int k_dp_publish(int* const* d_peer_flags, int n_peers, int slot, int me, int value, cudaStream_t st) {
+  dp_publish_kernel<<<1, 32, 0, st>>>(d_peer_flags, n_peers, slot, me, value);
   return static_cast<int>(cudaGetLastError());
 }
-int k_dp_wait(const int* flags, int n_ranks, int me, int value, cudaStream_t st) {
-  dp_wait_kernel<<<1, 32, 0, st>>>(flags, n_ranks, me, value);
+int k_dp_wait(const int* flags, int n_ranks, int slot, int me, int value, cudaStream_t st) {
+  dp_wait_kernel<<<1, 32, 0, st>>>(flags, n_ranks, slot, me, value);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -65,8 +65,11 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
 // first n_bcast segments are ALSO stored into the n_peers other GPUs' shadow arenas (same offsets) over NVLink.
 // k_dp_publish then writes `value` into slot `me` of every peer's flag array (d_peer_flags: DEVICE array of
 // peer-mapped pointers); k_dp_wait spins until every other rank's slot in the local array reached `value`.
-int k_dp_publish(int* const* d_peer_flags, int n_peers, int me, int value, cudaStream_t st);
-int k_dp_wait(const int* flags, int n_ranks, int me, int value, cudaStream_t st);
+// The flag array holds [slot][16 ranks] words (TFK_DP_FLAG_WORDS ints): slot 0 paces whole steps, slot 1 + l layers.
+constexpr int TFK_DP_FLAG_SLOTS = 66;
+constexpr int TFK_DP_FLAG_WORDS = TFK_DP_FLAG_SLOTS * 16;
+int k_dp_publish(int* const* d_peer_flags, int n_peers, int slot, int me, int value, cudaStream_t st);
+int k_dp_wait(const int* flags, int n_ranks, int slot, int me, int value, cudaStream_t st);
 
 // Batch-norm (reference: classifiers/activation.py:159 -> tf.contrib.layers.batch_norm defaults):
 // finalize per-column batch statistics from the GEMM epilogue's 32-row partials, update the moving
