@@ -275,7 +275,7 @@ int finish_params(tfk_handle* h, Plan& plan, const GemmSpec* s, int n, GemmParam
     return fail(h, TFK_ECUDA, "%s plan layer %d: %s", what, l, err);
   std::vector<int> key;
   if (gp->two_cta) {  // everything gemm_upload_tile_lists reads
-    key = {gp->total_tiles, gp->nprob};
+    key = {gp->total_tiles, gp->nprob, gp->a_resident};
     for (int i = 0; i < gp->nprob; ++i) {
       const GemmProblem& p = gp->p[i];
       const int f[7] = {p.tile_begin, p.tiles_m, p.tiles_n, p.kb_per_split, p.num_kb, p.nsplit, p.N};

@@ -42,8 +42,17 @@ struct SmemBars2 {
   uint64_t empty[STAGES2];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t a_full, a_empty;  // A-stationary launches: the resident A panel of the current run of tiles
   uint32_t tmem_base;
 };
+// A-stationary launches (one problem, K <= 7 k-blocks, e.g. the layer-0 forward 8192 x 440 -> 2048): a pair works through
+// CONSECUTIVE column tiles of one 256-row block, so its A panel (7 x 16 KB per CTA) is loaded once per run and stays in
+// the first 112 KB of the operand area; only B streams through a ring of RES_STAGES 16 KB slots behind it.  Such a tile
+// moves 224 KB instead of 448 KB per pair through L2 -> SM, which is what paces these short-K tiles.
+constexpr int RES_MAX_KB = 7;
+constexpr int RES_STAGES = 5;
+static_assert(RES_MAX_KB * A_TILE_BYTES + RES_STAGES * A_TILE_BYTES <= SLABS_OFF, "resident layout must fit the operand area");
+static_assert(RES_STAGES <= STAGES2, "the B ring reuses the full/empty barriers");
 static_assert(sizeof(SmemBars2) <= 256, "barrier block too large");
 
 struct SmemBars {
@@ -631,6 +640,22 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_
   }
 }
 
+// Called by every lane of epilogue warp `ew` before it waits for the accumulator: L1 prefetch of the lines the
+// epilogue will read with plain loads for this tile (layout as in epilogue_tile / epilogue_dispatch).
+__device__ __forceinline__ void epilogue_prefetch(const GemmProblem& pr, int m0, int n0, uint32_t ew, uint32_t lane, int chunks) {
+  if (pr.out_kind == OUT_BF16_SPLIT) return;  // (the hi+lo path is bound by its three MMA passes, not by the epilogue)
+  const uint32_t q = (ew + 2) & 3, part = ew >> 2;
+  const int c0 = static_cast<int>(part) * (chunks / 2), nch = chunks / 2;
+  if (static_cast<int>(lane) >= nch) return;
+  const int col0 = n0 + (c0 + static_cast<int>(lane)) * 32;  // lane i covers chunk c0 + i: 32 columns = one 128-byte line of floats
+  if (col0 >= pr.N) return;
+  if (pr.bias != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr.bias + col0));
+  if (pr.mask_bits_in != nullptr) {
+    const int row0 = m0 + static_cast<int>(q) * 32;
+    if (row0 < pr.M) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr.mask_bits_in + static_cast<size_t>(col0 >> 5) * pr.mask_bits_ld + row0));
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tfk_gemm_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -874,6 +899,8 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
         mbar_init(&bars->tmem_full[i], 1);   // multicast tcgen05.commit from the leader
         mbar_init(&bars->tmem_empty[i], 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
       }
+      mbar_init(&bars->a_full, 1);
+      mbar_init(&bars->a_empty, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -886,13 +913,56 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
   const uint32_t tmem_base = bars->tmem_base;
   pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
-  if (warp == 0) {
+  if (warp == 0 && P.a_resident) {
+    // ============================ TMA producer, A-stationary launch ============================
+    if (lane == 0) {
+      const GemmProblem& pr = P.p[0];
+      const uint32_t ring = smem_base + RES_MAX_KB * A_TILE_BYTES;
+      const uint32_t tx_b = 2 * 2 * MN_ATOM_BYTES;  // 128 B rows per CTA (two 64-row atoms or one 128-row box), both CTAs
+      uint32_t stage = 0, phase = 0;
+      int cur_m = -1, run = -1;
+      int next_entry = __ldg(my_list);
+      for (int it = 0;; ++it) {
+        const int entry = next_entry;
+        if (entry < 0) break;
+        next_entry = __ldg(my_list + it + 1);
+        const TileCoord tc = decode_tile(P, entry & kTileMask);
+        const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128;
+        const int nb = tc.n_blk * BN + static_cast<int>(rank) * 128;
+        if (tc.m_blk != cur_m) {  // a new run: replace the resident A panel once the MMAs of the previous run have read it
+          cur_m = tc.m_blk;
+          ++run;
+          mbar_wait(&bars->a_empty, (run & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&bars->a_full, 2 * pr.num_kb * A_TILE_BYTES);
+          for (int kb = 0; kb < pr.num_kb; ++kb)
+            tma_load_2d_2sm(smem_base + kb * A_TILE_BYTES, &pr.tmA[0], &bars->a_full, kb * BK, m0);
+        }
+        for (int kb = 0; kb < pr.num_kb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&bars->full[stage], tx_b);
+          const uint32_t sb = ring + stage * A_TILE_BYTES;
+          if (pr.b_mn) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sb + j * MN_ATOM_BYTES, &pr.tmB[0], &bars->full[stage], nb + 64 * j, kb * BK);
+          } else {
+            tma_load_2d_2sm(sb, &pr.tmB[0], &bars->full[stage], kb * BK, nb);
+          }
+          if (++stage == RES_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ============================ TMA producer (both CTAs) ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      int next_entry = __ldg(my_list);
       for (int it = 0;; ++it) {
-        const int entry = __ldg(my_list + it);
+        const int entry = next_entry;
         if (entry < 0) break;
+        next_entry = __ldg(my_list + it + 1);  // in flight while this tile is processed (a list ends with -1 inside its row)
         const TileCoord tc = decode_tile(P, entry & kTileMask);
         const GemmProblem& pr = P.p[tc.p];
         const int half = entry >> kHalfShift;  // 0: 256 columns, 1 / 2: left / right 128 columns
@@ -937,13 +1007,61 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
         }
       }
     }
+  } else if (warp == 1 && P.a_resident) {
+    // ============================ MMA issuer, A-stationary launch (leader CTA only) ============================
+    if (lane == 0 && rank == 0) {
+      const GemmProblem& pr = P.p[0];
+      const uint32_t ring = smem_base + RES_MAX_KB * A_TILE_BYTES;
+      const uint32_t idesc = make_idesc_bf16(256, BN, 0, pr.b_mn);
+      const uint32_t b_lbo = pr.b_mn ? MN_ATOM_BYTES : 16u, b_kadv = pr.b_mn ? 2048u : 32u;
+      uint32_t stage = 0, phase = 0;
+      int cur_m = -1, run = -1;
+      int next_entry = __ldg(my_list);
+      for (int it = 0;; ++it) {
+        const int entry = next_entry;
+        if (entry < 0) break;
+        next_entry = __ldg(my_list + it + 1);
+        const TileCoord tc = decode_tile(P, entry & kTileMask);
+        if (tc.m_blk != cur_m) {
+          cur_m = tc.m_blk;
+          ++run;
+          mbar_wait(&bars->a_full, run & 1);
+          tc_fence_after();
+        }
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        for (int kb = 0; kb < pr.num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + kb * A_TILE_BYTES;
+          const uint32_t sb = ring + stage * A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(tmem_acc, make_smem_desc_sw128(sa + k * 32u, 16u, 1024u),
+                          make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&bars->empty[stage]);
+          if (++stage == RES_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&bars->tmem_full[as]);
+        // last tile of its run: once these MMAs are done the producers may overwrite the A panel
+        const bool run_ends = next_entry < 0 || decode_tile(P, next_entry & kTileMask).m_blk != cur_m;
+        if (run_ends) umma_commit_2sm(&bars->a_empty);
+      }
+    }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ============================
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
+      int next_entry = __ldg(my_list);
       for (int it = 0;; ++it) {
-        const int entry = __ldg(my_list + it);
+        const int entry = next_entry;
         if (entry < 0) break;
+        next_entry = __ldg(my_list + it + 1);
         const TileCoord tc = decode_tile(P, entry & kTileMask);
         const GemmProblem& pr = P.p[tc.p];
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -997,16 +1115,22 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
     // ============================ epilogue warps (both CTAs, own 128 rows) ============================
     const uint32_t ew = warp - 2;
     const uint32_t slabs = smem_base + SLABS_OFF;
+    int next_entry = __ldg(my_list);
     for (int it = 0;; ++it) {
-      const int entry = __ldg(my_list + it);
+      const int entry = next_entry;
       if (entry < 0) break;
+      next_entry = __ldg(my_list + it + 1);
       const TileCoord tc = decode_tile(P, entry & kTileMask);
       const GemmProblem& pr = P.p[tc.p];
       const int half = entry >> kHalfShift;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN + (half == 2 ? 128 : 0);
+      // while the accumulator is still being computed: pull this warp's share of the per-column / per-row epilogue
+      // operands (bias, gradient-pass bits) towards L1 — their first-touch L2 latency was the largest single stall of the
+      // epilogue warps (profiles/r2f_ncu_l0fwd_stalls.txt)
+      epilogue_prefetch(pr, m0, n0, ew, lane, half ? BN / 64 : BN / 32);
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN + (half == 2 ? 128 : 0);
       if (m0 < pr.M)  // a ragged last pair-tile may leave the peer CTA without rows (CTA-uniform)
         epilogue_dispatch(pr, tmem_base + as * BN, m0, n0, ew, lane, slabs, half ? BN / 64 : BN / 32);
       tc_fence_before();
@@ -1274,6 +1398,15 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     tile_begin += p.tiles_m * p.tiles_n * p.ksplit;
   }
   out->total_tiles = tile_begin;
+  out->a_resident = 0;
+  if (two_cta && nspec == 1) {
+    const GemmSpec& s0 = specs[0];
+    const GemmProblem& p0 = out->p[0];
+    static const char* off = getenv("TFK_GEMM_A_RESIDENT");  // "0": never (A/B measurements)
+    if (!(off && off[0] == '0') && !s0.a_mn && s0.nsplit == 1 && p0.ksplit == 1 && p0.num_kb <= RES_MAX_KB && s0.N % BN == 0 &&
+        p0.tiles_n >= 2)
+      out->a_resident = 1;
+  }
   return 0;
 }
 
@@ -1310,6 +1443,23 @@ void gemm_schedule_tile_lists(const GemmParams* params, int num_sms, std::vector
   int pairs = num_sms / 2;
   if (pairs > 2 * total) pairs = 2 * total;
   if (pairs < 1) pairs = 1;
+  if (params->a_resident) {
+    // A-stationary launch: tile index = m_blk * tiles_n + n_blk, so CONSECUTIVE indices share their A panel; every pair
+    // gets one contiguous range (sizes differ by at most one tile), whole tiles only
+    if (pairs > total) pairs = total;
+    const int base = total / pairs, rem = total % pairs;
+    const int stride = base + 2;
+    std::vector<int> flat(static_cast<size_t>(pairs) * stride, -1);
+    int t = 0;
+    for (int p = 0; p < pairs; ++p) {
+      const int n = base + (p < rem ? 1 : 0);
+      for (int i = 0; i < n; ++i) flat[static_cast<size_t>(p) * stride + i] = t++;
+    }
+    *pairs_out = pairs;
+    *stride_out = stride;
+    flat_out->swap(flat);
+    return;
+  }
   // Cost model, in half-k-block units: k-extent (MMA time) + a constant for the epilogue.  A tile may be scheduled
   // as two 128-column halves (M256 N128 MMAs): used for tiles whose right half lies outside N, to shorten a partly
   // filled last round (256 equal tiles on 74 pairs: 3 + 0.8 rounds instead of 4) and for launches with few tiles.

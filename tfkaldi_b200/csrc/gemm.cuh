@@ -147,6 +147,7 @@ struct alignas(64) GemmParams {
   int* sched;  // [2]: {next tile counter, finished-CTA counter}; self-resetting (1-CTA kernel)
   // CTA-pair kernel (cta_group::2, 256x256 tiles): static longest-first work lists, one per pair
   int two_cta;
+  int a_resident;  // CTA-pair kernel: A-stationary launch (one short-K problem; consecutive column tiles reuse the A panel)
   int num_pairs;
   int list_stride;
   const int* tile_list;  // device [num_pairs, list_stride], -1 terminated

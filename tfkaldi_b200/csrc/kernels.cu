@@ -429,7 +429,10 @@ struct AdamSegs {
 };
 // blockIdx.y = segment (the whole arena on one GPU; a rank's slice of every layer + the small
 // replicated region under sharded data parallelism)
-__global__ void __launch_bounds__(256)
+// 128-thread blocks at <= 64 registers: one such block fits on an SM NEXT TO a resident GEMM CTA (320 threads x 168
+// registers leave 11.7 K of the 64 K registers; the GEMM takes all the shared memory, this kernel uses none), so the
+// per-layer updates launched on the side stream really run under the backward kernels instead of in the gaps between them.
+__global__ void __launch_bounds__(128)
 adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
             uint2* __restrict__ w_hi, uint2* __restrict__ w_lo, const AdamSegs segs, const double* __restrict__ acc,
             float lr_t, float b1, float b2, float eps) {
@@ -1218,10 +1221,10 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
       longest = segs.cnt4[i] > longest ? segs.cnt4[i] : longest;
     }
     if (longest == 0) continue;
-    int per_seg = 148 * 8 / segs.n;
-    if (per_seg < 8) per_seg = 8;
-    dim3 grid(grid_for(longest, 256, per_seg), segs.n);
-    adam_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(g),
+    int per_seg = 148 * 16 / segs.n;
+    if (per_seg < 16) per_seg = 16;
+    dim3 grid(grid_for(longest, 128, per_seg), segs.n);
+    adam_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(g),
                                       reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                       reinterpret_cast<uint2*>(w_hi), reinterpret_cast<uint2*>(w_lo), segs, acc, lr_t,
                                       beta1, beta2, eps);

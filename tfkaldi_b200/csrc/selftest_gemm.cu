@@ -466,6 +466,8 @@ int main(int argc, char** argv) {
         {"fwd bn-stats split", 300, 512, 440, 0, 1, 3, OUT_BF16_SPLIT, true, false, false, true, false},
         {"fwd relu+dropout", 256, 512, 128, 0, 1, 1, OUT_BF16, true, true, false, false, true},
         {"fwd many tiles (persistent loop)", 2048, 2048, 256, 0, 1, 1, OUT_BF16, true, true, false, false, false},
+        {"fwd A-stationary ragged M, K=440", 700, 768, 440, 0, 1, 1, OUT_BF16, true, true, false, false, false},
+        {"fwd A-stationary K/K f32, 5 runs", 1100, 512, 300, 0, 0, 1, OUT_F32, true, false, false, false, false},
         {"wgrad split-K x5 ragged", 440, 300, 8192 + 40, 1, 1, 1, OUT_F32_REDADD, false, false, false, false, false, 5},
         {"wgrad split-K x3 bf16x3", 256, 256, 2048, 1, 1, 3, OUT_F32_REDADD, false, false, false, false, false, 3},
     };
