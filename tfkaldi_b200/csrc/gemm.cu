@@ -224,6 +224,254 @@ struct EpiView<F_ALL> {
   using type = const GemmProblem&;
 };
 
+// Which instantiation serves a problem (decided on the host, gemm_build_params): a lean one when the problem uses no
+// feature outside its mask, else the generic one.
+enum EpiVariant : int { EV_GENERIC = 0, EV_FWD_RELU_BITS, EV_FWD_STATS, EV_DGRAD_BITS_COLSUM, EV_DGRAD_BN, EV_PLAIN };
+constexpr uint32_t kFeatOf[] = {F_ALL, F_BIAS | F_RELU | F_BITS_OUT, F_BIAS | F_STATS, F_BITS_IN | F_COLSUM,
+                                F_MASK_RELU | F_COLSUM | F_COLSUM2, F_BIAS};
+
+// Everything between the accumulator read and the store of one 32-column chunk: the fused FFLayer arithmetic
+// (classifiers/layer.py:52-56 forward; its tf.gradients twin backward) on v[j] = element (row, col0 + j).
+template <uint32_t FEAT, typename E>
+__device__ __forceinline__ void epilogue_math(const E& e, float (&v)[32], int col0, int row, bool row_ok, uint32_t lane,
+                                              uint32_t q, int m0) {
+  float yv[32];  // stored forward output of the layer below (live only in instantiations with F_COLSUM2)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+  if ((FEAT & F_BIAS) && e.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(bp + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
+  }
+  if ((FEAT & F_STATS) && e.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float z = row_ok ? v[j] : 0.f;
+      s1[j] = z;
+      s2[j] = z * z;
+    }
+    const float t1 = warp_transpose_reduce(s1, lane);
+    const float t2 = warp_transpose_reduce(s2, lane);
+    const int col = col0 + static_cast<int>(lane);
+    if (col < e.N) {
+      const size_t o = static_cast<size_t>((m0 >> 5) + q) * e.stat_ld + col;
+      e.stat_sum[o] = t1;
+      e.stat_sq[o] = t2;
+    }
+  }
+  if ((FEAT & F_RELU) && e.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if ((FEAT & F_ACT_SMOOTH) && e.act == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+  } else if ((FEAT & F_ACT_SMOOTH) && e.act == 3) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+  }
+  uint32_t keepword = 0xFFFFFFFFu;  // dropout keep decisions of this chunk's 32 columns (all ones without dropout)
+  if ((FEAT & F_DROPOUT) && e.drop_thr != 0u) {
+    keepword = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // one Philox call per 8 columns
+      const Philox4 rnd =
+          philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
+                        static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32));
+      const uint32_t keep = dropout_keep_bits(rnd, e.drop_thr);
+      keepword |= keep << (8 * j);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[8 * j + k] = ((keep >> k) & 1u) ? v[8 * j + k] * e.keep_inv : 0.f;
+    }
+  }
+  if ((FEAT & F_BITS_OUT) && e.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
+    uint32_t word;
+    if (e.mask_nonzero) {
+      // identity non-linearity: the gradient passes wherever dropout kept the unit — the keep decision itself, not
+      // "stored value != 0" (a kept pre-activation that is exactly 0 would otherwise lose its gradient)
+      word = keepword;
+    } else {
+      uint32_t b4[4] = {0u, 0u, 0u, 0u};  // four independent chains (two epilogue warps per scheduler: ILP is all there is)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) b4[j & 3] |= (v[j] > 0.f ? 1u : 0u) << j;
+      word = (b4[0] | b4[1]) | (b4[2] | b4[3]);
+    }
+    if (row_ok) e.mask_bits_out[static_cast<size_t>(col0 >> 5) * e.mask_bits_ld + row] = word;
+  }
+  if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u) {  // backward: re-draw the forward pass's keep decisions
+    keepword = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      keepword |= dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
+                                                  static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32)),
+                                    e.bwd_drop_thr) << (8 * j);
+  }
+  if ((FEAT & F_BITS_IN) && e.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
+    const uint32_t bits = row_ok ? __ldg(e.mask_bits_in + static_cast<size_t>(col0 >> 5) * e.mask_bits_ld + row) : 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * e.scale : 0.f;
+  }
+  if ((FEAT & F_MASK_DERIV) && e.mask_src != nullptr && e.deriv != 0) {
+    // backward of sigmoid / tanh (+dropout) from the stored forward output a = f(z) * dropmask / keep
+    const float keep = 1.0f / e.scale;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const bool ok = row_ok && (col0 + j) < e.N;
+      const size_t o = static_cast<size_t>(row) * e.mask_ld + col0 + j;
+      float a = ok ? __bfloat162float(e.mask_src[o]) : 0.f;
+      if (ok && e.mask_src_lo != nullptr) a += __bfloat162float(e.mask_src_lo[o]);
+      const float y = a * keep;
+      const float d = e.deriv == 1 ? y * (1.0f - y) : 1.0f - y * y;
+      const bool dropped = e.dropout_in_chain && (((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u) ? ((keepword >> j) & 1u) == 0u : a == 0.f);
+      v[j] = (ok && !dropped) ? v[j] * d * e.scale : 0.f;
+    }
+  } else
+  if ((FEAT & F_MASK_RELU) && e.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
+    const __nv_bfloat16* mp = e.mask_src + static_cast<size_t>(row) * e.mask_ld + col0;
+    const bool keep_y = (FEAT & F_COLSUM2) && e.bn_from_y;  // the batch-norm sums below want the values, not just the signs
+    if (row_ok && col0 + 32 <= e.N) {
+      const uint4* mp4 = reinterpret_cast<const uint4*>(mp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 m = __ldg(mp4 + j);
+        const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+          bool plo = (e.mask_nonzero || (lo & 0x8000u) == 0) && (lo & 0x7FFFu) != 0;
+          bool phi = (e.mask_nonzero || (hi & 0x8000u) == 0) && (hi & 0x7FFFu) != 0;
+          if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u && e.mask_nonzero) {  // identity + dropout: the keep bit decides
+            plo = (keepword >> (8 * j + 2 * k)) & 1u;
+            phi = (keepword >> (8 * j + 2 * k + 1)) & 1u;
+          }
+          v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * e.scale : 0.f;
+          v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * e.scale : 0.f;
+          if (keep_y) {
+            yv[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
+            yv[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+          }
+        }
+      }
+      if (keep_y && e.mask_src_lo != nullptr) {  // bf16x3: the stored output is hi + lo
+        const uint4* lp4 = reinterpret_cast<const uint4*>(e.mask_src_lo + static_cast<size_t>(row) * e.mask_ld + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 m = __ldg(lp4 + j);
+          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            yv[8 * j + 2 * k + 0] += __uint_as_float(w[k] << 16);
+            yv[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool ok = row_ok && (col0 + j) < e.N;
+        float mv = ok ? __bfloat162float(mp[j]) : 0.f;
+        bool pass = e.mask_nonzero ? (mv != 0.f) : (mv > 0.f);
+        if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u && e.mask_nonzero) pass = ok && ((keepword >> j) & 1u);
+        v[j] = pass ? v[j] * e.scale : 0.f;
+        if (keep_y) {
+          if (ok && e.mask_src_lo != nullptr)
+            mv += __bfloat162float(e.mask_src_lo[static_cast<size_t>(row) * e.mask_ld + col0 + j]);
+          yv[j] = mv;
+        }
+      }
+    }
+  }
+
+  if ((FEAT & F_COLSUM) && e.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = row_ok ? v[j] : 0.f;
+    const float tot = warp_transpose_reduce(t, lane);
+    const int col = col0 + static_cast<int>(lane);
+    if (col < e.N) e.colsum_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
+  }
+  if ((FEAT & F_COLSUM2) && e.colsum2_part != nullptr && e.bn_from_y) {
+    // batch-norm backward, column sums of dY * xhat WITHOUT reading z: the layer below stored y = f(xhat + beta) * keepmask
+    // / keep with f = relu or identity, and dY (v, already masked) is zero wherever y is, so on every element that
+    // counts xhat = y * keep - beta — from the values the mask was just derived from (no extra operand traffic in a
+    // kernel whose main loop is bound by L2 -> SM delivery)
+    float t[32];
+    const float keep = 1.0f / e.scale;
+    const float4* bp = reinterpret_cast<const float4*>(e.bn_beta + col0);  // padded to a multiple of 256 floats
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 be = __ldg(bp + j);
+      t[4 * j + 0] = v[4 * j + 0] * (yv[4 * j + 0] * keep - be.x);
+      t[4 * j + 1] = v[4 * j + 1] * (yv[4 * j + 1] * keep - be.y);
+      t[4 * j + 2] = v[4 * j + 2] * (yv[4 * j + 2] * keep - be.z);
+      t[4 * j + 3] = v[4 * j + 3] * (yv[4 * j + 3] * keep - be.w);
+    }
+    const float tot = warp_transpose_reduce(t, lane);
+    const int col = col0 + static_cast<int>(lane);
+    if (col < e.N) e.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
+  } else if ((FEAT & F_COLSUM2) && e.colsum2_part != nullptr) {  // general form: xhat = (z - mean) * rstd from the stored z
+    float t[32];
+    const bool full = row_ok && col0 + 32 <= e.N;
+    const __nv_bfloat16* zp = e.bn_z_hi + static_cast<size_t>(row) * e.bn_z_ld + col0;
+    if (full) {
+      const uint4* z4 = reinterpret_cast<const uint4*>(zp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 zz = __ldg(z4 + j);
+        const uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
+          t[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+        }
+      }
+      if (e.bn_z_lo != nullptr) {
+        const uint4* l4 = reinterpret_cast<const uint4*>(e.bn_z_lo + static_cast<size_t>(row) * e.bn_z_ld + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 zz = __ldg(l4 + j);
+          const uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            t[8 * j + 2 * k + 0] += __uint_as_float(w[k] << 16);
+            t[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool ok = row_ok && (col0 + j) < e.N;
+        float z = ok ? __bfloat162float(zp[j]) : 0.f;
+        if (ok && e.bn_z_lo != nullptr)
+          z += __bfloat162float(e.bn_z_lo[static_cast<size_t>(row) * e.bn_z_ld + col0 + j]);
+        t[j] = z;
+      }
+    }
+    const float4* mp = reinterpret_cast<const float4*>(e.bn_mean + col0);  // padded to a multiple of 256 floats
+    const float4* rp = reinterpret_cast<const float4*>(e.bn_rstd + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 mu = __ldg(mp + j), rs = __ldg(rp + j);
+      t[4 * j + 0] = row_ok ? v[4 * j + 0] * ((t[4 * j + 0] - mu.x) * rs.x) : 0.f;
+      t[4 * j + 1] = row_ok ? v[4 * j + 1] * ((t[4 * j + 1] - mu.y) * rs.y) : 0.f;
+      t[4 * j + 2] = row_ok ? v[4 * j + 2] * ((t[4 * j + 2] - mu.z) * rs.z) : 0.f;
+      t[4 * j + 3] = row_ok ? v[4 * j + 3] * ((t[4 * j + 3] - mu.w) * rs.w) : 0.f;
+    }
+    const float tot = warp_transpose_reduce(t, lane);
+    const int col = col0 + static_cast<int>(lane);
+    if (col < e.N) e.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
+  }
+
+}
+
 template <int OUT, uint32_t FEAT>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tmem_acc, int m0,
                                               int n0, uint32_t q, uint32_t lane, uint32_t slab_a,
@@ -234,6 +482,51 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
   const uint32_t lane_taddr = tmem_acc + ((q * 32u) << 16);
   const uint32_t row_off = lane * 128u;
   const uint32_t sw = lane & 7u;
+
+  if constexpr (OUT == OUT_BF16 && (FEAT == kFeatOf[EV_FWD_RELU_BITS] || FEAT == kFeatOf[EV_DGRAD_BITS_COLSUM])) {
+    // The two hottest bf16 instantiations (pairing the batch-norm ones spills): the two chunks of a 64-column store group are read from TMEM together and their
+    // arithmetic is one straight-line block, so the compiler interleaves two independent instruction streams — with two
+    // epilogue warps per scheduler, instruction-level parallelism is the only latency hiding there is
+    // (profiles/r2g_ncu_l0fwd_stalls.txt: a third of the epilogue's samples were fixed-latency dependency stalls).
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 2) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= e.N) break;  // warp-uniform
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(c * 32), r0);
+      tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(c * 32 + 32), r1);
+      tmem_ld_wait();
+      float v0[32], v1[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v0[j] = __uint_as_float(r0[j]);
+        v1[j] = __uint_as_float(r1[j]);
+      }
+      epilogue_math<FEAT>(e, v0, col0, row, row_ok, lane, q, m0);
+      epilogue_math<FEAT>(e, v1, col0 + 32, row, row_ok, lane, q, m0);
+      if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the slab
+      __syncwarp();
+      const uint32_t slab = slab_a + row_off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                     "r"(pack_bf16x2(v0[8 * j + 0], v0[8 * j + 1])), "r"(pack_bf16x2(v0[8 * j + 2], v0[8 * j + 3])),
+                     "r"(pack_bf16x2(v0[8 * j + 4], v0[8 * j + 5])), "r"(pack_bf16x2(v0[8 * j + 6], v0[8 * j + 7]))
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + ((static_cast<uint32_t>(4 + j) ^ sw) << 4)),
+                     "r"(pack_bf16x2(v1[8 * j + 0], v1[8 * j + 1])), "r"(pack_bf16x2(v1[8 * j + 2], v1[8 * j + 3])),
+                     "r"(pack_bf16x2(v1[8 * j + 4], v1[8 * j + 5])), "r"(pack_bf16x2(v1[8 * j + 6], v1[8 * j + 7]))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&pr.tmD[0], slab_a, col0, m0 + static_cast<int>(q * 32));
+        tma_commit_group();
+      }
+    }
+    return;
+  }
 
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
@@ -248,241 +541,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    float yv[32];  // stored forward output of the layer below (live only in instantiations with F_COLSUM2)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) yv[j] = 0.f;
-
-    if ((FEAT & F_BIAS) && e.bias != nullptr) {  // bias buffers are padded to a multiple of 256 floats
-      const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(bp + j);
-        v[4 * j + 0] += b.x;
-        v[4 * j + 1] += b.y;
-        v[4 * j + 2] += b.z;
-        v[4 * j + 3] += b.w;
-      }
-    }
-    if ((FEAT & F_STATS) && e.stat_sum != nullptr) {  // batch-norm statistics of z = xW + b over this warp's 32 rows
-      float s1[32], s2[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float z = row_ok ? v[j] : 0.f;
-        s1[j] = z;
-        s2[j] = z * z;
-      }
-      const float t1 = warp_transpose_reduce(s1, lane);
-      const float t2 = warp_transpose_reduce(s2, lane);
-      const int col = col0 + static_cast<int>(lane);
-      if (col < e.N) {
-        const size_t o = static_cast<size_t>((m0 >> 5) + q) * e.stat_ld + col;
-        e.stat_sum[o] = t1;
-        e.stat_sq[o] = t2;
-      }
-    }
-    if ((FEAT & F_RELU) && e.act == 1) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if ((FEAT & F_ACT_SMOOTH) && e.act == 2) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
-    } else if ((FEAT & F_ACT_SMOOTH) && e.act == 3) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-    }
-    uint32_t keepword = 0xFFFFFFFFu;  // dropout keep decisions of this chunk's 32 columns (all ones without dropout)
-    if ((FEAT & F_DROPOUT) && e.drop_thr != 0u) {
-      keepword = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {  // one Philox call per 8 columns
-        const Philox4 rnd =
-            philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
-                          static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32));
-        const uint32_t keep = dropout_keep_bits(rnd, e.drop_thr);
-        keepword |= keep << (8 * j);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[8 * j + k] = ((keep >> k) & 1u) ? v[8 * j + k] * e.keep_inv : 0.f;
-      }
-    }
-    if ((FEAT & F_BITS_OUT) && e.mask_bits_out != nullptr) {  // remember which units pass gradient: 1 bit each, coalesced store
-      uint32_t word;
-      if (e.mask_nonzero) {
-        // identity non-linearity: the gradient passes wherever dropout kept the unit — the keep decision itself, not
-        // "stored value != 0" (a kept pre-activation that is exactly 0 would otherwise lose its gradient)
-        word = keepword;
-      } else {
-        uint32_t b4[4] = {0u, 0u, 0u, 0u};  // four independent chains (two epilogue warps per scheduler: ILP is all there is)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) b4[j & 3] |= (v[j] > 0.f ? 1u : 0u) << j;
-        word = (b4[0] | b4[1]) | (b4[2] | b4[3]);
-      }
-      if (row_ok) e.mask_bits_out[static_cast<size_t>(col0 >> 5) * e.mask_bits_ld + row] = word;
-    }
-    if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u) {  // backward: re-draw the forward pass's keep decisions
-      keepword = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        keepword |= dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(col0 >> 3) + j, static_cast<uint32_t>(row), 0u, 0u,
-                                                    static_cast<uint32_t>(e.seed), static_cast<uint32_t>(e.seed >> 32)),
-                                      e.bwd_drop_thr) << (8 * j);
-    }
-    if ((FEAT & F_BITS_IN) && e.mask_bits_in != nullptr) {  // backward of relu(+dropout) from the forward pass's bit mask
-      const uint32_t bits = row_ok ? __ldg(e.mask_bits_in + static_cast<size_t>(col0 >> 5) * e.mask_bits_ld + row) : 0u;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * e.scale : 0.f;
-    }
-    if ((FEAT & F_MASK_DERIV) && e.mask_src != nullptr && e.deriv != 0) {
-      // backward of sigmoid / tanh (+dropout) from the stored forward output a = f(z) * dropmask / keep
-      const float keep = 1.0f / e.scale;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const bool ok = row_ok && (col0 + j) < e.N;
-        const size_t o = static_cast<size_t>(row) * e.mask_ld + col0 + j;
-        float a = ok ? __bfloat162float(e.mask_src[o]) : 0.f;
-        if (ok && e.mask_src_lo != nullptr) a += __bfloat162float(e.mask_src_lo[o]);
-        const float y = a * keep;
-        const float d = e.deriv == 1 ? y * (1.0f - y) : 1.0f - y * y;
-        const bool dropped = e.dropout_in_chain && (((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u) ? ((keepword >> j) & 1u) == 0u : a == 0.f);
-        v[j] = (ok && !dropped) ? v[j] * d * e.scale : 0.f;
-      }
-    } else
-    if ((FEAT & F_MASK_RELU) && e.mask_src != nullptr) {  // backward of relu(+dropout): pass where the forward output was > 0
-      const __nv_bfloat16* mp = e.mask_src + static_cast<size_t>(row) * e.mask_ld + col0;
-      const bool keep_y = (FEAT & F_COLSUM2) && e.bn_from_y;  // the batch-norm sums below want the values, not just the signs
-      if (row_ok && col0 + 32 <= e.N) {
-        const uint4* mp4 = reinterpret_cast<const uint4*>(mp);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 m = __ldg(mp4 + j);
-          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-            const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
-            bool plo = (e.mask_nonzero || (lo & 0x8000u) == 0) && (lo & 0x7FFFu) != 0;
-            bool phi = (e.mask_nonzero || (hi & 0x8000u) == 0) && (hi & 0x7FFFu) != 0;
-            if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u && e.mask_nonzero) {  // identity + dropout: the keep bit decides
-              plo = (keepword >> (8 * j + 2 * k)) & 1u;
-              phi = (keepword >> (8 * j + 2 * k + 1)) & 1u;
-            }
-            v[8 * j + 2 * k + 0] = plo ? v[8 * j + 2 * k + 0] * e.scale : 0.f;
-            v[8 * j + 2 * k + 1] = phi ? v[8 * j + 2 * k + 1] * e.scale : 0.f;
-            if (keep_y) {
-              yv[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
-              yv[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
-            }
-          }
-        }
-        if (keep_y && e.mask_src_lo != nullptr) {  // bf16x3: the stored output is hi + lo
-          const uint4* lp4 = reinterpret_cast<const uint4*>(e.mask_src_lo + static_cast<size_t>(row) * e.mask_ld + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 m = __ldg(lp4 + j);
-            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              yv[8 * j + 2 * k + 0] += __uint_as_float(w[k] << 16);
-              yv[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = row_ok && (col0 + j) < e.N;
-          float mv = ok ? __bfloat162float(mp[j]) : 0.f;
-          bool pass = e.mask_nonzero ? (mv != 0.f) : (mv > 0.f);
-          if ((FEAT & F_BWD_PHILOX) && e.bwd_drop_thr != 0u && e.mask_nonzero) pass = ok && ((keepword >> j) & 1u);
-          v[j] = pass ? v[j] * e.scale : 0.f;
-          if (keep_y) {
-            if (ok && e.mask_src_lo != nullptr)
-              mv += __bfloat162float(e.mask_src_lo[static_cast<size_t>(row) * e.mask_ld + col0 + j]);
-            yv[j] = mv;
-          }
-        }
-      }
-    }
-
-    if ((FEAT & F_COLSUM) && e.colsum_part != nullptr) {  // column sums of what is about to be stored (bias gradient below)
-      float t[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = row_ok ? v[j] : 0.f;
-      const float tot = warp_transpose_reduce(t, lane);
-      const int col = col0 + static_cast<int>(lane);
-      if (col < e.N) e.colsum_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
-    }
-    if ((FEAT & F_COLSUM2) && e.colsum2_part != nullptr && e.bn_from_y) {
-      // batch-norm backward, column sums of dY * xhat WITHOUT reading z: the layer below stored y = f(xhat + beta) * keepmask
-      // / keep with f = relu or identity, and dY (v, already masked) is zero wherever y is, so on every element that
-      // counts xhat = y * keep - beta — from the values the mask was just derived from (no extra operand traffic in a
-      // kernel whose main loop is bound by L2 -> SM delivery)
-      float t[32];
-      const float keep = 1.0f / e.scale;
-      const float4* bp = reinterpret_cast<const float4*>(e.bn_beta + col0);  // padded to a multiple of 256 floats
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 be = __ldg(bp + j);
-        t[4 * j + 0] = v[4 * j + 0] * (yv[4 * j + 0] * keep - be.x);
-        t[4 * j + 1] = v[4 * j + 1] * (yv[4 * j + 1] * keep - be.y);
-        t[4 * j + 2] = v[4 * j + 2] * (yv[4 * j + 2] * keep - be.z);
-        t[4 * j + 3] = v[4 * j + 3] * (yv[4 * j + 3] * keep - be.w);
-      }
-      const float tot = warp_transpose_reduce(t, lane);
-      const int col = col0 + static_cast<int>(lane);
-      if (col < e.N) e.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
-    } else if ((FEAT & F_COLSUM2) && e.colsum2_part != nullptr) {  // general form: xhat = (z - mean) * rstd from the stored z
-      float t[32];
-      const bool full = row_ok && col0 + 32 <= e.N;
-      const __nv_bfloat16* zp = e.bn_z_hi + static_cast<size_t>(row) * e.bn_z_ld + col0;
-      if (full) {
-        const uint4* z4 = reinterpret_cast<const uint4*>(zp);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 zz = __ldg(z4 + j);
-          const uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            t[8 * j + 2 * k + 0] = __uint_as_float(w[k] << 16);
-            t[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
-          }
-        }
-        if (e.bn_z_lo != nullptr) {
-          const uint4* l4 = reinterpret_cast<const uint4*>(e.bn_z_lo + static_cast<size_t>(row) * e.bn_z_ld + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 zz = __ldg(l4 + j);
-            const uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              t[8 * j + 2 * k + 0] += __uint_as_float(w[k] << 16);
-              t[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = row_ok && (col0 + j) < e.N;
-          float z = ok ? __bfloat162float(zp[j]) : 0.f;
-          if (ok && e.bn_z_lo != nullptr)
-            z += __bfloat162float(e.bn_z_lo[static_cast<size_t>(row) * e.bn_z_ld + col0 + j]);
-          t[j] = z;
-        }
-      }
-      const float4* mp = reinterpret_cast<const float4*>(e.bn_mean + col0);  // padded to a multiple of 256 floats
-      const float4* rp = reinterpret_cast<const float4*>(e.bn_rstd + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 mu = __ldg(mp + j), rs = __ldg(rp + j);
-        t[4 * j + 0] = row_ok ? v[4 * j + 0] * ((t[4 * j + 0] - mu.x) * rs.x) : 0.f;
-        t[4 * j + 1] = row_ok ? v[4 * j + 1] * ((t[4 * j + 1] - mu.y) * rs.y) : 0.f;
-        t[4 * j + 2] = row_ok ? v[4 * j + 2] * ((t[4 * j + 2] - mu.z) * rs.z) : 0.f;
-        t[4 * j + 3] = row_ok ? v[4 * j + 3] * ((t[4 * j + 3] - mu.w) * rs.w) : 0.f;
-      }
-      const float tot = warp_transpose_reduce(t, lane);
-      const int col = col0 + static_cast<int>(lane);
-      if (col < e.N) e.colsum2_part[static_cast<size_t>((m0 >> 5) + q) * e.colsum_ld + col] = tot;
-    }
+    epilogue_math<FEAT>(e, v, col0, row, row_ok, lane, q, m0);
 
     if constexpr (OUT == OUT_F32 || OUT == OUT_F32_REDADD) {
       if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the slab
@@ -580,12 +639,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
     }
   }
 }
-
-// Which instantiation serves a problem (decided on the host, gemm_build_params): a lean one when the problem uses no
-// feature outside its mask, else the generic one.
-enum EpiVariant : int { EV_GENERIC = 0, EV_FWD_RELU_BITS, EV_FWD_STATS, EV_DGRAD_BITS_COLSUM, EV_DGRAD_BN, EV_PLAIN };
-constexpr uint32_t kFeatOf[] = {F_ALL, F_BIAS | F_RELU | F_BITS_OUT, F_BIAS | F_STATS, F_BITS_IN | F_COLSUM,
-                                F_MASK_RELU | F_COLSUM | F_COLSUM2, F_BIAS};
 
 // Tile-level dispatch shared by both kernels.  `ew` = epilogue warp index 0..7.
 __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_t tmem_acc, int m0, int n0,
@@ -1115,7 +1168,18 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
     // ============================ epilogue warps (both CTAs, own 128 rows) ============================
     const uint32_t ew = warp - 2;
     const uint32_t slabs = smem_base + SLABS_OFF;
+    // Pull this warp's share of a tile's per-column / per-row epilogue operands (bias, gradient-pass bits) towards L1 one
+    // whole tile ahead: their first-touch L2 latency was the largest single stall of the epilogue warps
+    // (profiles/r2f_ncu_l0fwd_stalls.txt), and when the epilogue is the pacing stage there is no idle wait to hide it in.
+    auto prefetch_for = [&](int entry_) {
+      if (entry_ < 0) return;
+      const TileCoord t_ = decode_tile(P, entry_ & kTileMask);
+      const int half_ = entry_ >> kHalfShift;
+      epilogue_prefetch(P.p[t_.p], t_.m_blk * 256 + static_cast<int>(rank) * 128, t_.n_blk * BN + (half_ == 2 ? 128 : 0), ew, lane,
+                        half_ ? BN / 64 : BN / 32);
+    };
     int next_entry = __ldg(my_list);
+    prefetch_for(next_entry);
     for (int it = 0;; ++it) {
       const int entry = next_entry;
       if (entry < 0) break;
@@ -1125,10 +1189,7 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
       const int half = entry >> kHalfShift;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN + (half == 2 ? 128 : 0);
-      // while the accumulator is still being computed: pull this warp's share of the per-column / per-row epilogue
-      // operands (bias, gradient-pass bits) towards L1 — their first-touch L2 latency was the largest single stall of the
-      // epilogue warps (profiles/r2f_ncu_l0fwd_stalls.txt)
-      epilogue_prefetch(pr, m0, n0, ew, lane, half ? BN / 64 : BN / 32);
+      prefetch_for(next_entry);
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       if (m0 < pr.M)  // a ragged last pair-tile may leave the peer CTA without rows (CTA-uniform)
