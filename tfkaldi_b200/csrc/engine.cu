@@ -504,19 +504,14 @@ int forward_range(tfk_handle* h, Plan& plan, int B, bool training, int first, bo
       TFK_LAUNCH(h, gemm_launch(gp, h->num_sms, st));
     }
     if (ly.hidden && ly.bn) {
-      TimerScope ts(h, st, TFK_TIMER_BN, 2);
-      if (training) {
-        TFK_LAUNCH(h, k_bn_finalize(h->bn_ps, h->bn_pq, (B + 31) / 32, ly.npad, ly.N, B, h->cfg.bn_eps,
-                                    h->cfg.bn_decay, ly.bn_mean, ly.bn_rstd, ly.moving_mean, ly.moving_var, st));
-      } else {
-        TFK_LAUNCH(h, k_bn_eval_stats(ly.moving_mean, ly.moving_var, ly.N, h->cfg.bn_eps, ly.bn_mean,
-                                      ly.bn_rstd, st));
-      }
+      TimerScope ts(h, st, TFK_TIMER_BN, 1);
       const bool l2 = h->cfg.l2_norm != 0;
       const float keep = (!l2 && training && h->cfg.keep_prob < 1.0f) ? h->cfg.keep_prob : 1.0f;
-      TFK_LAUNCH(h, k_bn_apply(ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd, h->P + ly.off_beta,
-                               act_code, keep, layer_seed(h, l),
-                               l2 ? ly.u_hi : h->act_hi[l + 1], l2 ? ly.u_lo : h->act_lo[l + 1], st));
+      // statistics + normalise + beta + non-linearity + dropout in one column-strip launch
+      TFK_LAUNCH(h, k_bn_fwd_strip(h->bn_ps, h->bn_pq, (B + 31) / 32, ly.npad, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, h->cfg.bn_eps,
+                                   h->cfg.bn_decay, training ? 1 : 0, ly.bn_mean, ly.bn_rstd, ly.moving_mean, ly.moving_var,
+                                   h->P + ly.off_beta, act_code, keep, layer_seed(h, l), l2 ? ly.u_hi : h->act_hi[l + 1],
+                                   l2 ? ly.u_lo : h->act_lo[l + 1], st));
     }
     if (ly.hidden && h->cfg.l2_norm) {
       TimerScope ts(h, st, TFK_TIMER_BN);
@@ -546,15 +541,15 @@ int backward_layer(tfk_handle* h, Plan& plan, int B, int l, cudaStream_t st,
   }
   if (ly.hidden && ly.bn) {  // d(bn output) -> d(linear output), plus dbeta
     TimerScope ts(h, st, TFK_TIMER_BN, 2);
-    if (fused_colsum && !h->cfg.l2_norm) {  // the dgrad epilogue of the layer above left the partial sums
-      TFK_LAUNCH(h, k_bn_bwd_finalize(h->bn_ps, h->bn_pq, (B + 31) / 32, ly.npad, ly.N, ly.ldn, ly.bn_sums,
-                                      h->G + ly.off_beta, st));
+    if (fused_colsum && !h->cfg.l2_norm) {  // the dgrad epilogue of the layer above left the partial sums: one strip launch
+      TFK_LAUNCH(h, k_bn_bwd_strip(h->bn_ps, h->bn_pq, (B + 31) / 32, ly.npad, dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N,
+                                   ly.bn_mean, ly.bn_rstd, h->G + ly.off_beta, st));
     } else {
       TFK_LAUNCH(h, k_bn_bwd_reduce(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
                                     h->ws, h->bn_counters, ly.bn_sums, h->G + ly.off_beta, st));
+      TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
+                                   ly.bn_sums, st));
     }
-    TFK_LAUNCH(h, k_bn_bwd_apply(dz_hi, dz_lo, ly.z_hi, ly.z_lo, ly.ldn, B, ly.N, ly.bn_mean, ly.bn_rstd,
-                                 ly.bn_sums, st));
   }
   // Bias gradient = column sums of dZ.  Under batch-norm it is identically zero: z = xW + b enters only through
   // z - mean_B(z), so sum_B dz = rstd * (sum dy - sum dy - mean(dy xhat) * sum xhat) = 0 (layer.py:52 feeding

@@ -1178,12 +1178,15 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
       epilogue_prefetch(P.p[t_.p], t_.m_blk * 256 + static_cast<int>(rank) * 128, t_.n_blk * BN + (half_ == 2 ? 128 : 0), ew, lane,
                         half_ ? BN / 64 : BN / 32);
     };
+    // list entries are read two tiles ahead so that neither the tile loop nor the prefetch below ever waits for one
     int next_entry = __ldg(my_list);
+    int next2_entry = next_entry >= 0 ? __ldg(my_list + 1) : -1;
     prefetch_for(next_entry);
     for (int it = 0;; ++it) {
       const int entry = next_entry;
       if (entry < 0) break;
-      next_entry = __ldg(my_list + it + 1);
+      next_entry = next2_entry;
+      next2_entry = next_entry >= 0 ? __ldg(my_list + it + 2) : -1;  // (a list ends with -1 inside its row)
       const TileCoord tc = decode_tile(P, entry & kTileMask);
       const GemmProblem& pr = P.p[tc.p];
       const int half = entry >> kHalfShift;

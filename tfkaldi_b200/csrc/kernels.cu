@@ -807,6 +807,227 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat1
   if (t == 0) counters[blockIdx.x] = 0u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column-strip batch-norm kernels: one block owns 16 columns and ALL rows.  It first finishes the column reductions of
+// its 16 columns from the per-32-row partials a GEMM epilogue wrote (a few KB, fixed summation order), then streams the
+// strip (16 bf16 = 32 bytes per row: whole sectors) through the element-wise transform.  One launch per layer and
+// direction instead of a tiny latency-bound `finalize` launch followed by an `apply` launch (the two finalize kernels
+// were 78 us of a C4 step: profiles/r2b_ncu_full_summary_c4_small_kernels.txt).
+constexpr int STRIP_COLS = 16;
+constexpr int STRIP_ROWS_IN_FLIGHT = 4;
+
+// forward: statistics (training: from the partials, with the moving-average update; eval: the moving statistics), then
+// y = f((z - mean) * rstd + beta) [* dropout]   (reference: classifiers/activation.py:159-161 -> nonlinearity -> 140-141)
+template <bool X3>
+__global__ void __launch_bounds__(256)
+bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups, int pld,
+                    const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N,
+                    float eps, float decay, int training, float* __restrict__ mean, float* __restrict__ rstd,
+                    float* __restrict__ mm, float* __restrict__ mv, const float* __restrict__ beta, int act,
+                    unsigned int drop_thr, float keep_inv, unsigned long long seed, __nv_bfloat16* __restrict__ y_hi,
+                    __nv_bfloat16* __restrict__ y_lo) {
+  __shared__ double sm[2][16][STRIP_COLS + 1];
+  __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_be[STRIP_COLS];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * STRIP_COLS;
+  {
+    const int cl = t & (STRIP_COLS - 1), gl = t >> 4;  // 16 columns x 16 group lanes
+    const int c = c0 + cl;
+    double s1 = 0.0, s2 = 0.0;
+    if (training && c < N) {
+      for (int g0 = gl; g0 < groups; g0 += 64) {  // four independent loads per array in flight
+        float a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = g0 + 16 * k;
+          a[k] = g < groups ? ps[static_cast<size_t>(g) * pld + c] : 0.f;
+          b[k] = g < groups ? pq[static_cast<size_t>(g) * pld + c] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          s1 += static_cast<double>(a[k]);
+          s2 += static_cast<double>(b[k]);
+        }
+      }
+    }
+    sm[0][gl][cl] = s1;
+    sm[1][gl][cl] = s2;
+    __syncthreads();
+    if (t < STRIP_COLS) {
+      const int cc = c0 + t;
+      float muf = 0.f, rsf = 0.f, bef = 0.f;
+      if (cc < N) {
+        if (training) {
+          double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {  // fixed order
+            a1 += sm[0][k][t];
+            a2 += sm[1][k][t];
+          }
+          const double mu = a1 / B;
+          double var = a2 / B - mu * mu;  // biased (no Bessel), as tf.nn.moments
+          if (var < 0.0) var = 0.0;
+          muf = static_cast<float>(mu);
+          const float varf = static_cast<float>(var);
+          rsf = rsqrtf(varf + eps);
+          mm[cc] -= (1.0f - decay) * (mm[cc] - muf);  // assign_moving_average
+          mv[cc] -= (1.0f - decay) * (mv[cc] - varf);
+        } else {
+          muf = mm[cc];
+          rsf = rsqrtf(mv[cc] + eps);
+        }
+        mean[cc] = muf;  // kept for the backward pass
+        rstd[cc] = rsf;
+        bef = beta[cc];
+      }
+      s_mu[t] = muf;
+      s_rs[t] = rsf;
+      s_be[t] = bef;
+    }
+    __syncthreads();
+  }
+  const int h = t & 1, rr = t >> 1;  // which 8 of the 16 columns, row within a 128-row sweep
+  const int c = c0 + 8 * h;
+  if (c >= ld) return;
+  float mu[8], rs[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mu[k] = s_mu[8 * h + k];
+    rs[k] = s_rs[8 * h + k];
+    be[k] = s_be[8 * h + k];
+  }
+  for (int r0 = rr; r0 < B; r0 += 128 * STRIP_ROWS_IN_FLIGHT) {
+    uint4 hv[STRIP_ROWS_IN_FLIGHT], lv[STRIP_ROWS_IN_FLIGHT];
+#pragma unroll
+    for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
+      const int r = r0 + 128 * u;
+      if (r < B) {
+        const size_t o = static_cast<size_t>(r) * ld + c;
+        hv[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+        if (X3) lv[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
+      const int r = r0 + 128 * u;
+      if (r >= B) continue;
+      float x[8];
+      unpack8(hv[u], lv[u], X3, x);
+      uint32_t keep = 0xFFu;
+      if (drop_thr != 0u)
+        keep = dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(c >> 3), static_cast<uint32_t>(r), 0u, 0u,
+                                               static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), drop_thr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float y = (x[k] - mu[k]) * rs[k] + be[k];
+        if (act == 1) y = fmaxf(y, 0.f);
+        else if (act == 2) y = 1.0f / (1.0f + expf(-y));
+        else if (act == 3) y = tanhf(y);
+        y = (c + k < N) ? y : 0.f;
+        x[k] = (drop_thr != 0u) ? (((keep >> k) & 1u) ? y * keep_inv : 0.f) : y;
+      }
+      store8(y_hi, X3 ? y_lo : nullptr, static_cast<size_t>(r) * ld + c, x);
+    }
+  }
+}
+
+// backward: m1 = mean_B(dy), m2 = mean_B(dy * xhat) from the dgrad epilogue's partials (and dbeta += sum_B dy), then
+// dz = rstd * (dy - m1 - xhat * m2) in place over dy
+template <bool X3>
+__global__ void __launch_bounds__(256)
+bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int groups, int pld,
+                    __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo, const __nv_bfloat16* __restrict__ z_hi,
+                    const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, float* __restrict__ g_beta) {
+  __shared__ float sm[2][16][STRIP_COLS + 1];
+  __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_m1[STRIP_COLS], s_m2[STRIP_COLS];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * STRIP_COLS;
+  {
+    const int cl = t & (STRIP_COLS - 1), gl = t >> 4;
+    const int c = c0 + cl;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < N) {
+      for (int g0 = gl; g0 < groups; g0 += 64) {
+        float a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = g0 + 16 * k;
+          a[k] = g < groups ? p1[static_cast<size_t>(g) * pld + c] : 0.f;
+          b[k] = g < groups ? p2[static_cast<size_t>(g) * pld + c] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          s1 += a[k];
+          s2 += b[k];
+        }
+      }
+    }
+    sm[0][gl][cl] = s1;
+    sm[1][gl][cl] = s2;
+    __syncthreads();
+    if (t < STRIP_COLS) {
+      const int cc = c0 + t;
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        t1 += sm[0][k][t];
+        t2 += sm[1][k][t];
+      }
+      const bool ok = cc < N;
+      if (ok) g_beta[cc] += t1;
+      const float invB = 1.0f / static_cast<float>(B);
+      s_m1[t] = ok ? t1 * invB : 0.f;
+      s_m2[t] = ok ? t2 * invB : 0.f;
+      s_mu[t] = ok ? mean[cc] : 0.f;
+      s_rs[t] = ok ? rstd[cc] : 0.f;
+    }
+    __syncthreads();
+  }
+  const int h = t & 1, rr = t >> 1;
+  const int c = c0 + 8 * h;
+  if (c >= ld) return;
+  float mu[8], rs[8], m1[8], m2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mu[k] = s_mu[8 * h + k];
+    rs[k] = s_rs[8 * h + k];
+    m1[k] = s_m1[8 * h + k];
+    m2[k] = s_m2[8 * h + k];
+  }
+  constexpr int R = X3 ? 2 : STRIP_ROWS_IN_FLIGHT;
+  for (int r0 = rr; r0 < B; r0 += 128 * R) {
+    uint4 dh[R], dl[R], zh[R], zl[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int r = r0 + 128 * u;
+      if (r < B) {
+        const size_t o = static_cast<size_t>(r) * ld + c;
+        dh[u] = *reinterpret_cast<const uint4*>(dy_hi + o);
+        zh[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+        if (X3) {
+          dl[u] = *reinterpret_cast<const uint4*>(dy_lo + o);
+          zl[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int r = r0 + 128 * u;
+      if (r >= B) continue;
+      float d[8], z[8];
+      unpack8(dh[u], dl[u], X3, d);
+      unpack8(zh[u], zl[u], X3, z);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (z[k] - mu[k]) * rs[k];
+        d[k] = (c + k < N) ? rs[k] * (d[k] - m1[k] - xh * m2[k]) : 0.f;
+      }
+      store8(dy_hi, X3 ? dy_lo : nullptr, static_cast<size_t>(r) * ld + c, d);
+    }
+  }
+}
+
 // Finishes the two column reductions of the batch-norm backward from the per-32-row partials the dgrad epilogue wrote
 // (GemmSpec::colsum_part / colsum2_part): sums[c] = sum_B dy, sums[ld + c] = sum_B dy * xhat, g_beta[c] += sum_B dy.
 // block = 32 columns x 8 group lanes, fixed summation order.
@@ -1281,6 +1502,32 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
   else
     bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, ws, counters,
                                                       sums, g_beta);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_fwd_strip(const float* part_sum, const float* part_sq, int groups, int pld, const __nv_bfloat16* z_hi,
+                   const __nv_bfloat16* z_lo, int ld, int B, int N, float eps, float decay, int training, float* mean, float* rstd,
+                   float* moving_mean, float* moving_var, const float* beta, int act, float keep, unsigned long long seed,
+                   __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
+  const int grid = (ld + STRIP_COLS - 1) / STRIP_COLS;
+  if (z_lo)
+    bn_fwd_strip_kernel<true><<<grid, 256, 0, st>>>(part_sum, part_sq, groups, pld, z_hi, z_lo, ld, B, N, eps, decay, training, mean,
+                                                     rstd, moving_mean, moving_var, beta, act, thr, 1.0f / keep, seed, y_hi, y_lo);
+  else
+    bn_fwd_strip_kernel<false><<<grid, 256, 0, st>>>(part_sum, part_sq, groups, pld, z_hi, z_lo, ld, B, N, eps, decay, training, mean,
+                                                      rstd, moving_mean, moving_var, beta, act, thr, 1.0f / keep, seed, y_hi, y_lo);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_bn_bwd_strip(const float* part_sum, const float* part_dot, int groups, int pld, __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo,
+                   const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
+                   float* g_beta, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int grid = (ld + STRIP_COLS - 1) / STRIP_COLS;
+  if (dy_lo)
+    bn_bwd_strip_kernel<true><<<grid, 256, 0, st>>>(part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
+  else
+    bn_bwd_strip_kernel<false><<<grid, 256, 0, st>>>(part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,

@@ -89,6 +89,17 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                     const float* rstd, float* ws, unsigned int* counters, float* sums, float* g_beta, cudaStream_t st);
 // dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy*xhat)), written in place over dy
+// Column-strip batch-norm passes (one launch per layer and direction): statistics from the GEMM epilogue's per-32-row
+// partials (part_* [groups, pld]; training: batch statistics + moving-average update, else the moving statistics),
+// then y = f((z - mean) * rstd + beta) [* dropout] over the whole [B, N] matrix; backward: dbeta += sum dy and
+// dz = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)) in place.  mean / rstd [N] are written by the forward for the backward.
+int k_bn_fwd_strip(const float* part_sum, const float* part_sq, int groups, int pld, const __nv_bfloat16* z_hi,
+                   const __nv_bfloat16* z_lo, int ld, int B, int N, float eps, float decay, int training, float* mean, float* rstd,
+                   float* moving_mean, float* moving_var, const float* beta, int act, float keep, unsigned long long seed,
+                   __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st);
+int k_bn_bwd_strip(const float* part_sum, const float* part_dot, int groups, int pld, __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo,
+                   const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
+                   float* g_beta, cudaStream_t st);
 // Batch-norm backward reductions from the dgrad epilogue's per-32-row partials (part_* [groups, pld]):
 // sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat, g_beta += sum_B dy.
 int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,
