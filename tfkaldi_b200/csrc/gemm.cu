@@ -1466,8 +1466,12 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
   if (two_cta && nspec == 1) {
     const GemmSpec& s0 = specs[0];
     const GemmProblem& p0 = out->p[0];
-    static const char* off = getenv("TFK_GEMM_A_RESIDENT");  // "0": never (A/B measurements)
-    if (!(off && off[0] == '0') && !s0.a_mn && s0.nsplit == 1 && p0.ksplit == 1 && p0.num_kb <= RES_MAX_KB && s0.N % BN == 0 &&
+    // Measured on the layer-0 forward (8192 x 440 -> 2048, profiles/r2i_selftest_l0.txt): 21.9 us A-stationary against
+    // 20.1 us with the ordinary ring + half-tile balancing — that launch is paced by its epilogue (stall summaries
+    // profiles/r2h_ncu_l0fwd_stalls.txt), not by operand delivery, so halving the operand traffic buys nothing while the
+    // contiguous tile ranges cost the half-tile load balancing.  Opt-in (TFK_GEMM_A_RESIDENT=1) until the epilogue is faster.
+    static const char* on = getenv("TFK_GEMM_A_RESIDENT");
+    if ((on && on[0] == '1') && !s0.a_mn && s0.nsplit == 1 && p0.ksplit == 1 && p0.num_kb <= RES_MAX_KB && s0.N % BN == 0 &&
         p0.tiles_n >= 2)
       out->a_resident = 1;
   }

@@ -12,6 +12,33 @@ namespace tfk {
 
 namespace {
 
+// Programmatic dependent launch for the small kernels between the GEMMs of a step.  A kernel launched through
+// launch_pdl() may be scheduled while its predecessor in the stream is still running (the GEMM kernels release their
+// dependents at their very start); it must call pdl_enter() before touching anything the predecessor wrote — it does so
+// first thing, so what overlaps is its launch latency (a few microseconds per launch, ~30 launches per batch-norm step).
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  static const bool pdl = [] {
+    const char* e = getenv("TFK_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -41,6 +68,7 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 __global__ void split_f32_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, int ld_dst, int rows, int cols,
                                  int vec_ok) {
+  pdl_enter();
   const int groups = ld_dst >> 2;
   const size_t total = static_cast<size_t>(rows) * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -71,6 +99,7 @@ __global__ void __launch_bounds__(256)
 splice_cmvn_kernel(const float* __restrict__ raw, const int32_t* __restrict__ utt_off, int num_utts,
                    const float* __restrict__ cmvn, int D, int k, int row_begin, int rows,
                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_dst) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= rows) return;
@@ -213,6 +242,7 @@ __global__ void __launch_bounds__(256)
 softmax_ce_stream_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels, int B,
                          int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
                          __nv_bfloat16* __restrict__ d_lo) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -308,6 +338,7 @@ softmax_ce_generic_kernel(const float* __restrict__ logits, int ld, const int32_
 
 __global__ void __launch_bounds__(1024) accum_loss_kernel(const float* __restrict__ row_loss, int B,
                                                           double* __restrict__ acc) {
+  pdl_enter();
   __shared__ double sm[1024];
   double s = 0.0;
   for (int i = threadIdx.x; i < B; i += 1024) s += static_cast<double>(row_loss[i]);
@@ -390,6 +421,7 @@ struct ColsumJobs {
   int groups, ld, cols, njobs;
 };
 __global__ void __launch_bounds__(256) colsum_finalize_kernel(const ColsumJobs J) {
+  pdl_enter();
   __shared__ float sm[8][32];
   const float* __restrict__ part = J.part[blockIdx.y];
   const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;  // 32 columns x 8 group lanes
@@ -826,6 +858,7 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
                     float* __restrict__ mm, float* __restrict__ mv, const float* __restrict__ beta, int act,
                     unsigned int drop_thr, float keep_inv, unsigned long long seed, __nv_bfloat16* __restrict__ y_hi,
                     __nv_bfloat16* __restrict__ y_lo) {
+  pdl_enter();
   __shared__ double sm[2][16][STRIP_COLS + 1];
   __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_be[STRIP_COLS];
   const int t = threadIdx.x;
@@ -870,14 +903,18 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
           muf = static_cast<float>(mu);
           const float varf = static_cast<float>(var);
           rsf = rsqrtf(varf + eps);
-          mm[cc] -= (1.0f - decay) * (mm[cc] - muf);  // assign_moving_average
-          mv[cc] -= (1.0f - decay) * (mv[cc] - varf);
+          if (blockIdx.y == 0) {  // every row split of a strip derives the same statistics; one of them records them
+            mm[cc] -= (1.0f - decay) * (mm[cc] - muf);  // assign_moving_average
+            mv[cc] -= (1.0f - decay) * (mv[cc] - varf);
+          }
         } else {
           muf = mm[cc];
           rsf = rsqrtf(mv[cc] + eps);
         }
-        mean[cc] = muf;  // kept for the backward pass
-        rstd[cc] = rsf;
+        if (blockIdx.y == 0) {
+          mean[cc] = muf;  // kept for the backward pass
+          rstd[cc] = rsf;
+        }
         bef = beta[cc];
       }
       s_mu[t] = muf;
@@ -896,11 +933,12 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
     rs[k] = s_rs[8 * h + k];
     be[k] = s_be[8 * h + k];
   }
-  for (int r0 = rr; r0 < B; r0 += 128 * STRIP_ROWS_IN_FLIGHT) {
+  for (int r0 = rr + 128 * static_cast<int>(blockIdx.y); r0 < B; r0 += 128 * STRIP_ROWS_IN_FLIGHT * static_cast<int>(gridDim.y)) {
     uint4 hv[STRIP_ROWS_IN_FLIGHT], lv[STRIP_ROWS_IN_FLIGHT];
+    const int rstep = 128 * static_cast<int>(gridDim.y);
 #pragma unroll
     for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
-      const int r = r0 + 128 * u;
+      const int r = r0 + rstep * u;
       if (r < B) {
         const size_t o = static_cast<size_t>(r) * ld + c;
         hv[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
@@ -909,7 +947,7 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
     }
 #pragma unroll
     for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
-      const int r = r0 + 128 * u;
+      const int r = r0 + rstep * u;
       if (r >= B) continue;
       float x[8];
       unpack8(hv[u], lv[u], X3, x);
@@ -939,6 +977,7 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
                     __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo, const __nv_bfloat16* __restrict__ z_hi,
                     const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N, const float* __restrict__ mean,
                     const float* __restrict__ rstd, float* __restrict__ g_beta) {
+  pdl_enter();
   __shared__ float sm[2][16][STRIP_COLS + 1];
   __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_m1[STRIP_COLS], s_m2[STRIP_COLS];
   const int t = threadIdx.x;
@@ -975,7 +1014,7 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
         t2 += sm[1][k][t];
       }
       const bool ok = cc < N;
-      if (ok) g_beta[cc] += t1;
+      if (ok && blockIdx.y == 0) g_beta[cc] += t1;
       const float invB = 1.0f / static_cast<float>(B);
       s_m1[t] = ok ? t1 * invB : 0.f;
       s_m2[t] = ok ? t2 * invB : 0.f;
@@ -996,11 +1035,12 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
     m2[k] = s_m2[8 * h + k];
   }
   constexpr int R = X3 ? 2 : STRIP_ROWS_IN_FLIGHT;
-  for (int r0 = rr; r0 < B; r0 += 128 * R) {
+  const int rstep = 128 * static_cast<int>(gridDim.y);
+  for (int r0 = rr + 128 * static_cast<int>(blockIdx.y); r0 < B; r0 += rstep * R) {
     uint4 dh[R], dl[R], zh[R], zl[R];
 #pragma unroll
     for (int u = 0; u < R; ++u) {
-      const int r = r0 + 128 * u;
+      const int r = r0 + rstep * u;
       if (r < B) {
         const size_t o = static_cast<size_t>(r) * ld + c;
         dh[u] = *reinterpret_cast<const uint4*>(dy_hi + o);
@@ -1013,7 +1053,7 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
     }
 #pragma unroll
     for (int u = 0; u < R; ++u) {
-      const int r = r0 + 128 * u;
+      const int r = r0 + rstep * u;
       if (r >= B) continue;
       float d[8], z[8];
       unpack8(dh[u], dl[u], X3, d);
@@ -1240,6 +1280,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 decode_out_kernel(const float* __restrict__ logits, int ld, int T, int O, const float* __restrict__ prior,
                   float* __restrict__ out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= T) return;
@@ -1338,14 +1379,14 @@ int k_split_f32(const float* src, int ld_src, __nv_bfloat16* hi, __nv_bfloat16* 
   if (rows <= 0) return 0;
   const int vec_ok = (ld_src % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   const size_t total = static_cast<size_t>(rows) * (ld_dst >> 2);
-  split_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, ld_src, hi, lo, ld_dst, rows, cols, vec_ok);
+  launch_pdl(split_f32_kernel, dim3(grid_for(total, 256)), dim3(256), st, src, ld_src, hi, lo, ld_dst, rows, cols, vec_ok);
   return static_cast<int>(cudaGetLastError());
 }
 
 int k_splice_cmvn(const float* raw, const int32_t* utt_off, int num_utts, const float* cmvn, int D, int k,
                   int row_begin, int rows, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst, cudaStream_t st) {
   if (rows <= 0) return 0;
-  splice_cmvn_kernel<<<(rows + 7) / 8, 256, 0, st>>>(raw, utt_off, num_utts, cmvn, D, k, row_begin, rows, hi, lo, ld_dst);
+  launch_pdl(splice_cmvn_kernel, dim3((rows + 7) / 8), dim3(256), st, raw, utt_off, num_utts, cmvn, D, k, row_begin, rows, hi, lo, ld_dst);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1377,7 +1418,7 @@ int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int 
     return (e && strcmp(e, "regs") == 0) ? 1 : 0;
   }();
   if (variant == 0 && (ld & 3) == 0)
-    softmax_ce_stream_kernel<<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+    launch_pdl(softmax_ce_stream_kernel, dim3(grid), dim3(256), st, logits, ld, labels, B, O, row_loss, d_hi, d_lo);
   else if (ld <= 1024)
     softmax_ce_kernel<8><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
   else if (ld <= 2048)
@@ -1390,7 +1431,7 @@ int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int 
 }
 
 int k_accum_loss(const float* row_loss, int B, double* acc, cudaStream_t st) {
-  accum_loss_kernel<<<1, 1024, 0, st>>>(row_loss, B, acc);
+  launch_pdl(accum_loss_kernel, dim3(1), dim3(1024), st, row_loss, B, acc);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1417,7 +1458,7 @@ int k_colsum_finalize(const float* const* parts, float* const* outs, int njobs, 
     }
     J.groups = groups; J.ld = ld; J.cols = cols;
     dim3 grid((cols + 31) / 32, J.njobs);
-    colsum_finalize_kernel<<<grid, 256, 0, st>>>(J);
+    launch_pdl(colsum_finalize_kernel, grid, dim3(256), st, J);
   }
   return static_cast<int>(cudaGetLastError());
 }
@@ -1504,30 +1545,40 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
                                                       sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
+// strips x row splits: about four 256-thread blocks per SM (every row split re-derives its strip's statistics from the
+// same partials: a few KB from L2, identical results)
+static dim3 strip_grid(int ld, int B) {
+  const int strips = (ld + STRIP_COLS - 1) / STRIP_COLS;
+  int rs = (148 * 4 + strips - 1) / strips;
+  const int max_rs = (B + 127) / 128;
+  if (rs > max_rs) rs = max_rs;
+  if (rs < 1) rs = 1;
+  return dim3(strips, rs);
+}
 int k_bn_fwd_strip(const float* part_sum, const float* part_sq, int groups, int pld, const __nv_bfloat16* z_hi,
                    const __nv_bfloat16* z_lo, int ld, int B, int N, float eps, float decay, int training, float* mean, float* rstd,
                    float* moving_mean, float* moving_var, const float* beta, int act, float keep, unsigned long long seed,
                    __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st) {
   if (B <= 0) return 0;
   const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
-  const int grid = (ld + STRIP_COLS - 1) / STRIP_COLS;
+  const dim3 grid = strip_grid(ld, B);
   if (z_lo)
-    bn_fwd_strip_kernel<true><<<grid, 256, 0, st>>>(part_sum, part_sq, groups, pld, z_hi, z_lo, ld, B, N, eps, decay, training, mean,
-                                                     rstd, moving_mean, moving_var, beta, act, thr, 1.0f / keep, seed, y_hi, y_lo);
+    launch_pdl(bn_fwd_strip_kernel<true>, grid, dim3(256), st, part_sum, part_sq, groups, pld, z_hi, z_lo, ld, B, N, eps, decay,
+               training, mean, rstd, moving_mean, moving_var, beta, act, thr, 1.0f / keep, seed, y_hi, y_lo);
   else
-    bn_fwd_strip_kernel<false><<<grid, 256, 0, st>>>(part_sum, part_sq, groups, pld, z_hi, z_lo, ld, B, N, eps, decay, training, mean,
-                                                      rstd, moving_mean, moving_var, beta, act, thr, 1.0f / keep, seed, y_hi, y_lo);
+    launch_pdl(bn_fwd_strip_kernel<false>, grid, dim3(256), st, part_sum, part_sq, groups, pld, z_hi, z_lo, ld, B, N, eps, decay,
+               training, mean, rstd, moving_mean, moving_var, beta, act, thr, 1.0f / keep, seed, y_hi, y_lo);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_strip(const float* part_sum, const float* part_dot, int groups, int pld, __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo,
                    const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
                    float* g_beta, cudaStream_t st) {
   if (B <= 0) return 0;
-  const int grid = (ld + STRIP_COLS - 1) / STRIP_COLS;
+  const dim3 grid = strip_grid(ld, B);
   if (dy_lo)
-    bn_bwd_strip_kernel<true><<<grid, 256, 0, st>>>(part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
+    launch_pdl(bn_bwd_strip_kernel<true>, grid, dim3(256), st, part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
   else
-    bn_bwd_strip_kernel<false><<<grid, 256, 0, st>>>(part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
+    launch_pdl(bn_bwd_strip_kernel<false>, grid, dim3(256), st, part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,
@@ -1576,11 +1627,11 @@ int k_decode_out(const float* logits, int ld, int T, int O, const float* prior, 
   if (T <= 0) return 0;
   const int grid = (T + 7) / 8;
   if (ld <= 1024)
-    decode_out_kernel<8><<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+    launch_pdl(decode_out_kernel<8>, dim3(grid), dim3(256), st, logits, ld, T, O, prior, out);
   else if (ld <= 2048)
-    decode_out_kernel<16><<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+    launch_pdl(decode_out_kernel<16>, dim3(grid), dim3(256), st, logits, ld, T, O, prior, out);
   else if (ld <= 4096)
-    decode_out_kernel<32><<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
+    launch_pdl(decode_out_kernel<32>, dim3(grid), dim3(256), st, logits, ld, T, O, prior, out);
   else
     decode_out_generic_kernel<<<grid, 256, 0, st>>>(logits, ld, T, O, prior, out);
   return static_cast<int>(cudaGetLastError());
