@@ -475,7 +475,8 @@ __device__ __forceinline__ void epilogue_math(const E& e, float (&v)[32], int co
 template <int OUT, uint32_t FEAT>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tmem_acc, int m0,
                                               int n0, uint32_t q, uint32_t lane, uint32_t slab_a,
-                                              uint32_t slab_b, int c_begin, int c_end) {
+                                              uint32_t slab_b, int c_begin, int c_end,
+                                              float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f), bool has_bias_pre = false) {
   typename EpiView<FEAT>::type e(pr);
   const int row = m0 + static_cast<int>(q * 32 + lane);
   const bool row_ok = row < e.M;
@@ -502,8 +503,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
         v0[j] = __uint_as_float(r0[j]);
         v1[j] = __uint_as_float(r1[j]);
       }
-      epilogue_math<FEAT>(e, v0, col0, row, row_ok, lane, q, m0);
-      epilogue_math<FEAT>(e, v1, col0 + 32, row, row_ok, lane, q, m0);
+      if ((FEAT & F_BIAS) && has_bias_pre) {
+        // The warp's 128 bias values were loaded before the accumulator was waited for, four consecutive floats per lane
+        // (lane l: columns 4 l .. 4 l + 3 of the warp's column range); every lane needs all 32 of a chunk: broadcast.
+        // (Per-chunk loads of the bias stalled on first-touch L2 latency — each tile uses another 1 KB of it — and
+        // neither an L1 prefetch nor issuing them a tile ahead removed that: profiles/r2i_ncu_l0fwd_stalls.txt.)
+        const int lb = (c - c_begin) * 8;  // lane holding column 0 of chunk c
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v0[4 * j + 0] += __shfl_sync(0xffffffffu, bias_pre.x, lb + j);
+          v0[4 * j + 1] += __shfl_sync(0xffffffffu, bias_pre.y, lb + j);
+          v0[4 * j + 2] += __shfl_sync(0xffffffffu, bias_pre.z, lb + j);
+          v0[4 * j + 3] += __shfl_sync(0xffffffffu, bias_pre.w, lb + j);
+          v1[4 * j + 0] += __shfl_sync(0xffffffffu, bias_pre.x, lb + 8 + j);
+          v1[4 * j + 1] += __shfl_sync(0xffffffffu, bias_pre.y, lb + 8 + j);
+          v1[4 * j + 2] += __shfl_sync(0xffffffffu, bias_pre.z, lb + 8 + j);
+          v1[4 * j + 3] += __shfl_sync(0xffffffffu, bias_pre.w, lb + 8 + j);
+        }
+        epilogue_math<FEAT & ~F_BIAS>(e, v0, col0, row, row_ok, lane, q, m0);
+        epilogue_math<FEAT & ~F_BIAS>(e, v1, col0 + 32, row, row_ok, lane, q, m0);
+      } else {
+        epilogue_math<FEAT>(e, v0, col0, row, row_ok, lane, q, m0);
+        epilogue_math<FEAT>(e, v1, col0 + 32, row, row_ok, lane, q, m0);
+      }
       if (lane == 0) tma_wait_group_read<0>();  // the previous store has finished reading the slab
       __syncwarp();
       const uint32_t slab = slab_a + row_off;
@@ -642,7 +664,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& pr, uint32_t tm
 
 // Tile-level dispatch shared by both kernels.  `ew` = epilogue warp index 0..7.
 __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_t tmem_acc, int m0, int n0,
-                                                  uint32_t ew, uint32_t lane, uint32_t slabs, int chunks = BN / 32) {
+                                                  uint32_t ew, uint32_t lane, uint32_t slabs, int chunks = BN / 32,
+                                                  float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f), bool has_bias_pre = false) {
   // the hardware ties a warp to TMEM lanes 32 * (warp id % 4): epilogue warp ew is CTA warp ew + 2
   const uint32_t q = (ew + 2) & 3, part = ew >> 2;
   const uint32_t slab_a = slabs + ew * SLAB_BYTES;
@@ -665,7 +688,7 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmProblem& pr, uint32_
   const int c0 = static_cast<int>(part) * (chunks / 2), c1 = c0 + chunks / 2;  // chunks = 8 (256 cols) or 4 (half tile)
   switch (pr.out_kind * 8 + pr.epi_variant) {
     case OUT_BF16 * 8 + EV_FWD_RELU_BITS:
-      epilogue_tile<OUT_BF16, kFeatOf[EV_FWD_RELU_BITS]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
+      epilogue_tile<OUT_BF16, kFeatOf[EV_FWD_RELU_BITS]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1, bias_pre, has_bias_pre);
       break;
     case OUT_BF16 * 8 + EV_FWD_STATS:
       epilogue_tile<OUT_BF16, kFeatOf[EV_FWD_STATS]>(pr, tmem_acc, m0, n0, q, lane, slab_a, 0u, c0, c1);
@@ -1193,10 +1216,16 @@ tfk_gemm2_kernel(const __grid_constant__ GemmParams P) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int m0 = tc.m_blk * 256 + static_cast<int>(rank) * 128, n0 = tc.n_blk * BN + (half == 2 ? 128 : 0);
       prefetch_for(next_entry);
+      // forward tiles: this warp's bias values (its half of the tile's columns), in flight while the MMAs finish
+      const int chunks = half ? BN / 64 : BN / 32;
+      const bool bias_early = P.bias_shfl && pr.epi_variant == EV_FWD_RELU_BITS && pr.out_kind == OUT_BF16 && pr.bias != nullptr;
+      float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias_early && static_cast<int>(lane) < chunks * 4)  // chunks/2 chunks x 8 lanes per chunk
+        bias_pre = __ldg(reinterpret_cast<const float4*>(pr.bias + n0 + static_cast<int>(ew >> 2) * (chunks / 2) * 32) + lane);
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       if (m0 < pr.M)  // a ragged last pair-tile may leave the peer CTA without rows (CTA-uniform)
-        epilogue_dispatch(pr, tmem_base + as * BN, m0, n0, ew, lane, slabs, half ? BN / 64 : BN / 32);
+        epilogue_dispatch(pr, tmem_base + as * BN, m0, n0, ew, lane, slabs, chunks, bias_pre, bias_early);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[as]);
@@ -1462,6 +1491,8 @@ int gemm_build_params(const GemmSpec* specs, int nspec, int* sched, GemmParams* 
     tile_begin += p.tiles_m * p.tiles_n * p.ksplit;
   }
   out->total_tiles = tile_begin;
+  static const char* no_shfl = getenv("TFK_GEMM_BIAS_SHFL");  // "0": per-chunk bias loads (A/B measurements)
+  out->bias_shfl = (no_shfl && no_shfl[0] == '0') ? 0 : 1;
   out->a_resident = 0;
   if (two_cta && nspec == 1) {
     const GemmSpec& s0 = specs[0];

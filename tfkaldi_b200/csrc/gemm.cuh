@@ -147,6 +147,7 @@ struct alignas(64) GemmParams {
   int* sched;  // [2]: {next tile counter, finished-CTA counter}; self-resetting (1-CTA kernel)
   // CTA-pair kernel (cta_group::2, 256x256 tiles): static longest-first work lists, one per pair
   int two_cta;
+  int bias_shfl;   // forward tiles: bias loaded once per tile before the accumulator wait and broadcast by shuffles
   int a_resident;  // CTA-pair kernel: A-stationary launch (one short-K problem; consecutive column tiles reuse the A panel)
   int num_pairs;
   int list_stride;

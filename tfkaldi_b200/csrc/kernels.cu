@@ -23,7 +23,7 @@ __device__ __forceinline__ void pdl_enter() {
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
   static const bool pdl = [] {
-    const char* e = getenv("TFK_PDL");
+    const char* e = getenv("TFK_PDL_SMALL");
     return !(e && e[0] == '0');
   }();
   cudaLaunchConfig_t cfg = {};
