@@ -291,7 +291,7 @@ def run_ours(args):
     hbm_bytes = {
         "adam": (28 + sh) * nparams / max(world, 1) if world > 1 else (28 + sh) * nparams,
         "softmax_ce": B * O * (4 + sh),
-        "bn": (c["num_layers"] * B * c["hidden_dim"] * (2 * sh + 5 * sh)) if c["batch_norm"] else 0,
+        "bn": (c["num_layers"] * B * c["hidden_dim"] * (2 * sh + 3 * sh)) if c["batch_norm"] else 0,  # fwd: read z, write y; bwd: read dy + z, write dz
     }
     hbm = {}
     for k, nbytes in hbm_bytes.items():
