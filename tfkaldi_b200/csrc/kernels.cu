@@ -12,10 +12,12 @@ namespace tfk {
 
 namespace {
 
-// Programmatic dependent launch for the small kernels between the GEMMs of a step.  A kernel launched through
-// launch_pdl() may be scheduled while its predecessor in the stream is still running (the GEMM kernels release their
-// dependents at their very start); it must call pdl_enter() before touching anything the predecessor wrote — it does so
-// first thing, so what overlaps is its launch latency (a few microseconds per launch, ~30 launches per batch-norm step).
+// Programmatic dependent launch for the small kernels between the GEMMs of a step: OPT-IN (TFK_PDL_SMALL=1).  A kernel
+// launched through launch_pdl() with it may be scheduled while its predecessor in the stream is still running (the GEMM
+// kernels release their dependents at their very start); it calls pdl_enter() before touching anything the predecessor
+// wrote, so what overlaps is its launch latency.  Measured (one box, two repetitions, profiles/r2k_ab_pdl_small.txt): the
+// C4 step got SLOWER, 1.056 -> 1.144 ms, the C2 step 1-2 % slower — early-resident blocks of the small kernels sit on the
+// SMs the GEMM's last tiles still need and delay the next GEMM's CTAs — so the default is the plain launch.
 __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -24,7 +26,7 @@ template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
   static const bool pdl = [] {
     const char* e = getenv("TFK_PDL_SMALL");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -165,79 +167,11 @@ __global__ void double_to_float_kernel(const double* __restrict__ src, float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp per row; the row lives in registers (NV float4 per lane) so logits are read once.
-template <int NV>
-__global__ void __launch_bounds__(256)
-softmax_ce_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels, int B,
-                  int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
-                  __nv_bfloat16* __restrict__ d_lo) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= B) return;
-  const int nvec = ld >> 2;
-  const float4* zp = reinterpret_cast<const float4*>(logits + static_cast<size_t>(row) * ld);
-  float4 z[NV];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int idx = lane + 32 * i;
-    float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    if (idx < nvec) {
-      t = __ldg(zp + idx);
-      const int e = idx << 2;
-      if (e + 1 > O) t.x = -INFINITY;
-      if (e + 2 > O) t.y = -INFINITY;
-      if (e + 3 > O) t.z = -INFINITY;
-      if (e + 4 > O) t.w = -INFINITY;
-    }
-    z[i] = t;
-    mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
-  }
-  mx = warp_max(mx);
-  const int label = labels[row];
-  const bool label_ok = label >= 0 && label < O;
-  float sum = 0.f, zl = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int e = (lane + 32 * i) << 2;
-    if (label_ok && (label >> 2) == (lane + 32 * i)) {
-      const int t = label & 3;
-      zl = t == 0 ? z[i].x : t == 1 ? z[i].y : t == 2 ? z[i].z : z[i].w;
-    }
-    z[i].x = __expf(z[i].x - mx);
-    z[i].y = __expf(z[i].y - mx);
-    z[i].z = __expf(z[i].z - mx);
-    z[i].w = __expf(z[i].w - mx);
-    sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
-    (void)e;
-  }
-  sum = warp_sum(sum);
-  zl = warp_sum(zl);
-  if (lane == 0) row_loss[row] = label_ok ? (logf(sum) + mx - zl) : 0.f;
-  if (d_hi == nullptr) return;
-  const float inv = 1.0f / sum;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx >= nvec) continue;
-    const int e = idx << 2;
-    float p[4] = {z[i].x * inv, z[i].y * inv, z[i].z * inv, z[i].w * inv};
-    // softmax - onehot; an out-of-range label has an all-zero one-hot row (tf.one_hot): no loss term, but the op's
-    // gradient is still prob - labels = softmax (SoftmaxCrossEntropyWithLogits computes backprop = prob - labels)
-    if (label_ok && (label >> 2) == idx) p[label & 3] -= 1.0f;
-    uint2 h, l;
-    split2(p[0], p[1], h.x, l.x);
-    split2(p[2], p[3], h.y, l.y);
-    const size_t o = static_cast<size_t>(row) * ld + e;
-    *reinterpret_cast<uint2*>(d_hi + o) = h;
-    if (d_lo) *reinterpret_cast<uint2*>(d_lo + o) = l;
-  }
-}
-
 // One warp per row, two sweeps: (1) running max and sum of exp in ONE pass over the logits (online softmax), (2) the
 // row is read again — it was just brought into L1/L2 — to emit loss and gradient.  Nothing but a float4 lives in
-// registers between loads (~32 registers per thread against 80-174 for the row-in-registers variant above), so six to
-// eight blocks are resident per SM and enough loads are in flight to stream the logits at HBM speed.
+// registers between loads (~32 registers per thread; the round-1 kernels kept the whole row in registers: 80 registers at
+// 1936 pdf-ids, 174 at 3401 with 12 % occupancy), so six to eight blocks are resident per SM and enough loads are in
+// flight to stream the logits at HBM speed.
 __global__ void __launch_bounds__(256)
 softmax_ce_stream_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels, int B,
                          int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
@@ -295,7 +229,8 @@ softmax_ce_stream_kernel(const float* __restrict__ logits, int ld, const int32_t
       const int e = idx << 2;
       float p[4] = {e + 0 < O ? __expf(t[u].x - gmx) * inv : 0.f, e + 1 < O ? __expf(t[u].y - gmx) * inv : 0.f,
                     e + 2 < O ? __expf(t[u].z - gmx) * inv : 0.f, e + 3 < O ? __expf(t[u].w - gmx) * inv : 0.f};
-      // softmax - onehot; an out-of-range label has an all-zero one-hot row (see softmax_ce_kernel)
+      // softmax - onehot; an out-of-range label has an all-zero one-hot row (tf.one_hot): no loss term, but the op's
+      // gradient is still prob - labels = softmax (SoftmaxCrossEntropyWithLogits computes backprop = prob - labels)
       if (label_ok && (label >> 2) == idx) p[label & 3] -= 1.0f;
       uint2 h, l;
       split2(p[0], p[1], h.x, l.x);
@@ -304,35 +239,6 @@ softmax_ce_stream_kernel(const float* __restrict__ logits, int ld, const int32_t
       *reinterpret_cast<uint2*>(d_hi + o) = h;
       if (d_lo) *reinterpret_cast<uint2*>(d_lo + o) = l;
     }
-  }
-}
-
-// Any O: three passes over the row (the re-reads hit L1/L2).
-__global__ void __launch_bounds__(256)
-softmax_ce_generic_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ labels,
-                          int B, int O, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ d_hi,
-                          __nv_bfloat16* __restrict__ d_lo) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= B) return;
-  const float* zp = logits + static_cast<size_t>(row) * ld;
-  float mx = -INFINITY;
-  for (int e = lane; e < O; e += 32) mx = fmaxf(mx, zp[e]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int e = lane; e < O; e += 32) sum += expf(zp[e] - mx);
-  sum = warp_sum(sum);
-  const int label = labels[row];
-  const bool label_ok = label >= 0 && label < O;
-  if (lane == 0) row_loss[row] = label_ok ? (logf(sum) + mx - zp[label]) : 0.f;
-  if (d_hi == nullptr) return;
-  const float inv = 1.0f / sum;
-  for (int e = lane; e < ld; e += 32) {
-    float p = e < O ? expf(zp[e] - mx) * inv : 0.f;
-    if (label_ok && e == label) p -= 1.0f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(p);
-    d_hi[static_cast<size_t>(row) * ld + e] = h;
-    if (d_lo) d_lo[static_cast<size_t>(row) * ld + e] = __float2bfloat16_rn(p - __bfloat162float(h));
   }
 }
 
@@ -533,66 +439,6 @@ __global__ void dp_wait_kernel(const int* __restrict__ flags, int n_ranks, int s
   __threadfence_system();
 }
 
-// ------------------------------------------------------------------------------------------------
-// block = 32 columns x 32 group lanes; fixed summation order (lane-strided, then lanes 0..31) in double
-__global__ void __launch_bounds__(1024)
-bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups, int ld, int N,
-                   int rows, float eps, float decay, float* __restrict__ mean, float* __restrict__ rstd,
-                   float* __restrict__ mm, float* __restrict__ mv) {
-  __shared__ double sm[2][32][33];
-  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  double s1 = 0.0, s2 = 0.0;
-  if (c < N) {
-    int gidx = gl;
-    for (; gidx + 96 < groups; gidx += 128) {  // 8 loads in flight
-      float a[4], b[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a[k] = ps[static_cast<size_t>(gidx + 32 * k) * ld + c];
-        b[k] = pq[static_cast<size_t>(gidx + 32 * k) * ld + c];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        s1 += static_cast<double>(a[k]);
-        s2 += static_cast<double>(b[k]);
-      }
-    }
-    for (; gidx < groups; gidx += 32) {
-      s1 += static_cast<double>(ps[static_cast<size_t>(gidx) * ld + c]);
-      s2 += static_cast<double>(pq[static_cast<size_t>(gidx) * ld + c]);
-    }
-  }
-  sm[0][gl][cl] = s1;
-  sm[1][gl][cl] = s2;
-  __syncthreads();
-  if (gl != 0 || c >= N) return;
-  s1 = 0.0;
-  s2 = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < 32; ++k) {
-    s1 += sm[0][k][cl];
-    s2 += sm[1][k][cl];
-  }
-  const double mu = s1 / rows;
-  double var = s2 / rows - mu * mu;  // biased (no Bessel), as tf.nn.moments
-  if (var < 0.0) var = 0.0;
-  const float muf = static_cast<float>(mu), varf = static_cast<float>(var);
-  mean[c] = muf;
-  rstd[c] = rsqrtf(varf + eps);
-  if (mm) {  // assign_moving_average: mv -= (1 - decay) * (mv - value)
-    mm[c] -= (1.0f - decay) * (mm[c] - muf);
-    mv[c] -= (1.0f - decay) * (mv[c] - varf);
-  }
-}
-__global__ void bn_eval_stats_kernel(const float* __restrict__ mm, const float* __restrict__ mv, int N,
-                                     float eps, float* __restrict__ mean, float* __restrict__ rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  mean[c] = mm[c];
-  rstd[c] = rsqrtf(mv[c] + eps);
-}
-
 __device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t o, float (&x)[8]) {
   const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + o));
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
@@ -631,100 +477,7 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, bool has
   }
 }
 
-constexpr int BN_SPAN = 2048;  // columns per block of the element-wise BN kernels (256 threads x 8)
-constexpr int BN_ROWS = 4;     // rows in flight per thread
-
-// Block = a 2048-column span x a strided set of rows; thread = 8 columns, BN_ROWS rows in flight (raw 16-byte
-// fragments, transformed in place word by word).  A thread's per-column vectors are parked in shared memory
-// ([column-in-thread][thread]: conflict-free, private to the thread, so no barrier) instead of 24-32 registers and
-// fetched four columns at a time for all rows in flight.  Four blocks per SM; the grid is exactly one wave.
-template <bool X3>
-__global__ void __launch_bounds__(256, 4)
-bn_apply_kernel(const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld,
-                int B, int N, const float* __restrict__ mean, const float* __restrict__ rstd,
-                const float* __restrict__ beta, int relu, unsigned int drop_thr, float keep_inv,
-                unsigned long long seed, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
-  __shared__ float s_mu[8][256], s_rs[8][256], s_be[8][256];
-  const int cb = blockIdx.x * BN_SPAN;
-  const int t = threadIdx.x;
-  const int c = cb + (t << 3);
-  if (c >= ld) return;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {  // each thread stages its own eight columns: no barrier, conflict-free stores
-    const bool ok = c + k < N;
-    s_mu[k][t] = ok ? __ldg(mean + c + k) : 0.f;
-    s_rs[k][t] = ok ? __ldg(rstd + c + k) : 0.f;
-    s_be[k][t] = ok ? __ldg(beta + c + k) : 0.f;
-  }
-  const int step = static_cast<int>(gridDim.y);
-  for (int r0 = blockIdx.y; r0 < B; r0 += BN_ROWS * step) {
-    uint32_t hw[BN_ROWS][4], lw[BN_ROWS][4];
-#pragma unroll
-    for (int u = 0; u < BN_ROWS; ++u)
-      if (r0 + u * step < B) {
-        const size_t o = static_cast<size_t>(r0 + u * step) * ld + c;
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
-        hw[u][0] = h.x; hw[u][1] = h.y; hw[u][2] = h.z; hw[u][3] = h.w;
-        if (X3) {
-          const uint4 l = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
-          lw[u][0] = l.x; lw[u][1] = l.y; lw[u][2] = l.z; lw[u][3] = l.w;
-        }
-      }
-    uint32_t keepbits[BN_ROWS];
-#pragma unroll
-    for (int u = 0; u < BN_ROWS; ++u) {  // one Philox call decides the eight columns of a row
-      keepbits[u] = 0xFFu;
-      if (drop_thr != 0u && r0 + u * step < B)
-        keepbits[u] = dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(c >> 3), static_cast<uint32_t>(r0 + u * step), 0u, 0u,
-                                                      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), drop_thr);
-    }
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {  // columns c + 4 jj .. c + 4 jj + 3
-      float mu[4], rs[4], be[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        mu[i] = s_mu[4 * jj + i][t];
-        rs[i] = s_rs[4 * jj + i][t];
-        be[i] = s_be[4 * jj + i][t];
-      }
-#pragma unroll
-      for (int u = 0; u < BN_ROWS; ++u) {
-        const int r = r0 + u * step;
-        if (r < B) {
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const int j = 2 * jj + w;
-            float x[2] = {bf_lo(hw[u][j]), bf_hi(hw[u][j])};
-            if (X3) {
-              x[0] += bf_lo(lw[u][j]);
-              x[1] += bf_hi(lw[u][j]);
-            }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int i = 2 * w + e;
-              float y = (x[e] - mu[i]) * rs[i] + be[i];
-              if (relu == 1) y = fmaxf(y, 0.f);
-              else if (relu == 2) y = 1.0f / (1.0f + expf(-y));
-              else if (relu == 3) y = tanhf(y);
-              y = (c + 4 * jj + i < N) ? y : 0.f;
-              x[e] = (drop_thr != 0u) ? (((keepbits[u] >> (4 * jj + i)) & 1u) ? y * keep_inv : 0.f) : y;
-            }
-            split2(x[0], x[1], hw[u][j], lw[u][j]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < BN_ROWS; ++u) {
-      const int r = r0 + u * step;
-      if (r < B) {
-        const size_t o = static_cast<size_t>(r) * ld + c;
-        *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hw[u][0], hw[u][1], hw[u][2], hw[u][3]);
-        if (X3) *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lw[u][0], lw[u][1], lw[u][2], lw[u][3]);
-      }
-    }
-  }
-}
+constexpr int BN_SPAN = 2048;  // columns per block of bn_bwd_apply_kernel (256 threads x 8)
 
 // BN backward column reductions sum_B(dy) and sum_B(dy * xhat), one launch, deterministic.  ws layout [RS][2][ld].
 // A warp reads 256 consecutive columns (16 B per lane per array) of one row per load; a block's 8 warps stride over
@@ -1068,53 +821,8 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
   }
 }
 
-// Finishes the two column reductions of the batch-norm backward from the per-32-row partials the dgrad epilogue wrote
-// (GemmSpec::colsum_part / colsum2_part): sums[c] = sum_B dy, sums[ld + c] = sum_B dy * xhat, g_beta[c] += sum_B dy.
-// block = 32 columns x 8 group lanes, fixed summation order.
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int groups, int pld, int N, int ld,
-                       float* __restrict__ sums, float* __restrict__ g_beta) {
-  __shared__ float sm[2][8][32];
-  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float s1 = 0.f, s2 = 0.f;
-  if (c < N) {
-    int g = gl;
-    for (; g + 24 < groups; g += 32) {  // 8 independent loads in flight
-      float a[4], b[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a[k] = p1[static_cast<size_t>(g + 8 * k) * pld + c];
-        b[k] = p2[static_cast<size_t>(g + 8 * k) * pld + c];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        s1 += a[k];
-        s2 += b[k];
-      }
-    }
-    for (; g < groups; g += 8) {
-      s1 += p1[static_cast<size_t>(g) * pld + c];
-      s2 += p2[static_cast<size_t>(g) * pld + c];
-    }
-  }
-  sm[0][gl][cl] = s1;
-  sm[1][gl][cl] = s2;
-  __syncthreads();
-  if (gl == 0 && c < N) {
-    float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      t1 += sm[0][k][cl];
-      t2 += sm[1][k][cl];
-    }
-    sums[c] = t1;
-    sums[ld + c] = t2;
-    g_beta[c] += t1;
-  }
-}
-
-// dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy * xhat)), in place over dy; same tiling as bn_apply_kernel
+// dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy * xhat)), in place over dy, from the sums of bn_bwd_reduce_kernel
+// (the unit entry point tfk_fflayer_bwd and L2Norm chains; the training step uses bn_bwd_strip_kernel)
 template <bool X3>
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo,
@@ -1413,20 +1121,8 @@ int k_softmax_ce(const float* logits, int ld, const int32_t* labels, int B, int 
                  __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, cudaStream_t st) {
   if (B <= 0) return 0;
   const int grid = (B + 7) / 8;
-  static const int variant = [] {  // TFK_SOFTMAX=regs selects the row-in-registers kernels (A/B measurements)
-    const char* e = getenv("TFK_SOFTMAX");
-    return (e && strcmp(e, "regs") == 0) ? 1 : 0;
-  }();
-  if (variant == 0 && (ld & 3) == 0)
-    launch_pdl(softmax_ce_stream_kernel, dim3(grid), dim3(256), st, logits, ld, labels, B, O, row_loss, d_hi, d_lo);
-  else if (ld <= 1024)
-    softmax_ce_kernel<8><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
-  else if (ld <= 2048)
-    softmax_ce_kernel<16><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
-  else if (ld <= 4096)
-    softmax_ce_kernel<32><<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
-  else
-    softmax_ce_generic_kernel<<<grid, 256, 0, st>>>(logits, ld, labels, B, O, row_loss, d_hi, d_lo);
+  if ((ld & 3) != 0) return static_cast<int>(cudaErrorInvalidValue);  // rows are float4-aligned (ld is a multiple of 8)
+  launch_pdl(softmax_ce_stream_kernel, dim3(grid), dim3(256), st, logits, ld, labels, B, O, row_loss, d_hi, d_lo);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1503,34 +1199,6 @@ int k_dp_wait(const int* flags, int n_ranks, int slot, int me, int value, cudaSt
   return static_cast<int>(cudaGetLastError());
 }
 
-int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int ld, int N, int rows, float eps,
-                  float decay, float* mean, float* rstd, float* moving_mean, float* moving_var,
-                  cudaStream_t st) {
-  bn_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(part_sum, part_sq, groups, ld, N, rows, eps, decay, mean,
-                                                     rstd, moving_mean, moving_var);
-  return static_cast<int>(cudaGetLastError());
-}
-int k_bn_eval_stats(const float* moving_mean, const float* moving_var, int N, float eps, float* mean,
-                    float* rstd, cudaStream_t st) {
-  bn_eval_stats_kernel<<<(N + 255) / 256, 256, 0, st>>>(moving_mean, moving_var, N, eps, mean, rstd);
-  return static_cast<int>(cudaGetLastError());
-}
-int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
-               const float* rstd, const float* beta, int relu, float keep, unsigned long long seed,
-               __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st) {
-  if (B <= 0) return 0;
-  const unsigned int thr = keep < 1.0f ? dropout_threshold(keep) : 0u;
-  const int gx = (ld + BN_SPAN - 1) / BN_SPAN;
-  int gy = 148 * 4 / gx;  // one wave at four blocks per SM
-  gy = gy < 1 ? 1 : (gy > B ? B : gy);
-  if (z_lo)
-    bn_apply_kernel<true><<<dim3(gx, gy), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr, 1.0f / keep,
-                                                         seed, y_hi, y_lo);
-  else
-    bn_apply_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(z_hi, z_lo, ld, B, N, mean, rstd, beta, relu, thr, 1.0f / keep,
-                                                          seed, y_hi, y_lo);
-  return static_cast<int>(cudaGetLastError());
-}
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
                     float* ws, unsigned int* counters, float* sums, float* g_beta, cudaStream_t st) {
@@ -1579,11 +1247,6 @@ int k_bn_bwd_strip(const float* part_sum, const float* part_dot, int groups, int
     launch_pdl(bn_bwd_strip_kernel<true>, grid, dim3(256), st, part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
   else
     launch_pdl(bn_bwd_strip_kernel<false>, grid, dim3(256), st, part_sum, part_dot, groups, pld, dy_hi, dy_lo, z_hi, z_lo, ld, B, N, mean, rstd, g_beta);
-  return static_cast<int>(cudaGetLastError());
-}
-int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,
-                      float* g_beta, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<(N + 31) / 32, 256, 0, st>>>(part_sum, part_dot, groups, pld, N, ld, sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,

@@ -71,24 +71,12 @@ constexpr int TFK_DP_FLAG_WORDS = TFK_DP_FLAG_SLOTS * 16;
 int k_dp_publish(int* const* d_peer_flags, int n_peers, int slot, int me, int value, cudaStream_t st);
 int k_dp_wait(const int* flags, int n_ranks, int slot, int me, int value, cudaStream_t st);
 
-// Batch-norm (reference: classifiers/activation.py:159 -> tf.contrib.layers.batch_norm defaults):
-// finalize per-column batch statistics from the GEMM epilogue's 32-row partials, update the moving
-// averages (decay 0.999, biased variance), emit mean and rstd = rsqrt(var + eps).
-int k_bn_finalize(const float* part_sum, const float* part_sq, int groups, int ld, int N, int rows,
-                  float eps, float decay, float* mean, float* rstd, float* moving_mean,
-                  float* moving_var, cudaStream_t st);
-// mean/rstd from the moving statistics (eval mode)
-int k_bn_eval_stats(const float* moving_mean, const float* moving_var, int N, float eps, float* mean,
-                    float* rstd, cudaStream_t st);
-// y = dropout(act((z - mean) * rstd + beta)), act code `relu`: 0 none, 1 relu, 2 sigmoid, 3 tanh; z,y bf16 hi(+lo) [B, ld]
-int k_bn_apply(const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N,
-               const float* mean, const float* rstd, const float* beta, int relu, float keep,
-               unsigned long long seed, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t st);
+// Batch-norm (reference: classifiers/activation.py:159 -> tf.contrib.layers.batch_norm defaults: decay 0.999, eps 1e-3,
+// center without scale, biased variance in the moving average).
 // backward: sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat; g_beta += sum_B dy.  ws >= 256*ld floats
 int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                     const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                     const float* rstd, float* ws, unsigned int* counters, float* sums, float* g_beta, cudaStream_t st);
-// dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy*xhat)), written in place over dy
 // Column-strip batch-norm passes (one launch per layer and direction): statistics from the GEMM epilogue's per-32-row
 // partials (part_* [groups, pld]; training: batch statistics + moving-average update, else the moving statistics),
 // then y = f((z - mean) * rstd + beta) [* dropout] over the whole [B, N] matrix; backward: dbeta += sum dy and
@@ -100,10 +88,7 @@ int k_bn_fwd_strip(const float* part_sum, const float* part_sq, int groups, int 
 int k_bn_bwd_strip(const float* part_sum, const float* part_dot, int groups, int pld, __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo,
                    const __nv_bfloat16* z_hi, const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean, const float* rstd,
                    float* g_beta, cudaStream_t st);
-// Batch-norm backward reductions from the dgrad epilogue's per-32-row partials (part_* [groups, pld]):
-// sums[0..N) = sum_B dy, sums[ld..ld+N) = sum_B dy*xhat, g_beta += sum_B dy.
-int k_bn_bwd_finalize(const float* part_sum, const float* part_dot, int groups, int pld, int N, int ld, float* sums,
-                      float* g_beta, cudaStream_t st);
+// dz = rstd * (dy - mean_B(dy) - xhat * mean_B(dy*xhat)), written in place over dy, from k_bn_bwd_reduce's sums
 int k_bn_bwd_apply(__nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, const __nv_bfloat16* z_hi,
                    const __nv_bfloat16* z_lo, int ld, int B, int N, const float* mean,
                    const float* rstd, const float* sums, cudaStream_t st);
