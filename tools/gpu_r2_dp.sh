@@ -19,10 +19,15 @@ except Exception as e:
 PY
 }
 run overlap TFK_X=1
-run overlap_unbounded TFK_DP_RUNAHEAD=0
 run serial TFK_DP_OVERLAP=0
-run serial_unbounded TFK_DP_OVERLAP=0 TFK_DP_RUNAHEAD=0
-if [ "$N" = "8" ]; then run allreduce TFK_DP_MODE=allreduce; fi
+if [ "$N" = "8" ]; then
+  run allreduce TFK_DP_MODE=allreduce
+  run overlap_again TFK_X=1
+  run serial_again TFK_DP_OVERLAP=0
+else
+  run overlap_unbounded TFK_DP_RUNAHEAD=0
+  run serial_unbounded TFK_DP_OVERLAP=0 TFK_DP_RUNAHEAD=0
+fi
 echo "== bench --gpus 1 (same box)"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity-mode > gpurun_out/bench_1gpu_${TAG}.json 2>/dev/null; python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_1gpu_${TAG}.json")); print("1gpu value %.3e" % d["value"], d["timing"]["windows_ms_per_step"])
