@@ -604,7 +604,7 @@ constexpr int STRIP_ROWS_IN_FLIGHT = 4;
 // forward: statistics (training: from the partials, with the moving-average update; eval: the moving statistics), then
 // y = f((z - mean) * rstd + beta) [* dropout]   (reference: classifiers/activation.py:159-161 -> nonlinearity -> 140-141)
 template <bool X3>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups, int pld,
                     const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N,
                     float eps, float decay, int training, float* __restrict__ mean, float* __restrict__ rstd,
@@ -616,6 +616,32 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
   __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_be[STRIP_COLS];
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * STRIP_COLS;
+  // streaming role of this thread: 8 of the strip's 16 columns, one row per 128-row sweep.  Its first rows are
+  // requested (and their dropout decisions drawn) BEFORE the statistics are reduced: neither depends on them, and the
+  // reduction below is two dependent round trips to L2 during which the block would otherwise have nothing in flight.
+  const int h = t & 1, rr = t >> 1;
+  const int c = c0 + 8 * h;
+  const bool active = c < ld;
+  const int rstep = 128 * static_cast<int>(gridDim.y);
+  const int r_first = rr + 128 * static_cast<int>(blockIdx.y);
+  uint4 hv[STRIP_ROWS_IN_FLIGHT], lv[STRIP_ROWS_IN_FLIGHT];
+  uint32_t keepb[STRIP_ROWS_IN_FLIGHT];
+  auto load_batch = [&](int r0) {
+#pragma unroll
+    for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
+      const int r = r0 + rstep * u;
+      keepb[u] = 0xFFu;
+      if (active && r < B) {
+        const size_t o = static_cast<size_t>(r) * ld + c;
+        hv[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+        if (X3) lv[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+        if (drop_thr != 0u)
+          keepb[u] = dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(c >> 3), static_cast<uint32_t>(r), 0u, 0u,
+                                                     static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), drop_thr);
+      }
+    }
+  };
+  load_batch(r_first);
   {
     const int cl = t & (STRIP_COLS - 1), gl = t >> 4;  // 16 columns x 16 group lanes
     const int c = c0 + cl;
@@ -676,9 +702,7 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
     }
     __syncthreads();
   }
-  const int h = t & 1, rr = t >> 1;  // which 8 of the 16 columns, row within a 128-row sweep
-  const int c = c0 + 8 * h;
-  if (c >= ld) return;
+  if (!active) return;
   float mu[8], rs[8], be[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -686,28 +710,15 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
     rs[k] = s_rs[8 * h + k];
     be[k] = s_be[8 * h + k];
   }
-  for (int r0 = rr + 128 * static_cast<int>(blockIdx.y); r0 < B; r0 += 128 * STRIP_ROWS_IN_FLIGHT * static_cast<int>(gridDim.y)) {
-    uint4 hv[STRIP_ROWS_IN_FLIGHT], lv[STRIP_ROWS_IN_FLIGHT];
-    const int rstep = 128 * static_cast<int>(gridDim.y);
-#pragma unroll
-    for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
-      const int r = r0 + rstep * u;
-      if (r < B) {
-        const size_t o = static_cast<size_t>(r) * ld + c;
-        hv[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
-        if (X3) lv[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
-      }
-    }
+  for (int r0 = r_first; r0 < B; r0 += rstep * STRIP_ROWS_IN_FLIGHT) {
+    if (r0 != r_first) load_batch(r0);
 #pragma unroll
     for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
       const int r = r0 + rstep * u;
       if (r >= B) continue;
       float x[8];
       unpack8(hv[u], lv[u], X3, x);
-      uint32_t keep = 0xFFu;
-      if (drop_thr != 0u)
-        keep = dropout_keep_bits(philox4x32_10(static_cast<uint32_t>(c >> 3), static_cast<uint32_t>(r), 0u, 0u,
-                                               static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)), drop_thr);
+      const uint32_t keep = keepb[u];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float y = (x[k] - mu[k]) * rs[k] + be[k];
@@ -725,7 +736,7 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
 // backward: m1 = mean_B(dy), m2 = mean_B(dy * xhat) from the dgrad epilogue's partials (and dbeta += sum_B dy), then
 // dz = rstd * (dy - m1 - xhat * m2) in place over dy
 template <bool X3>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int groups, int pld,
                     __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo, const __nv_bfloat16* __restrict__ z_hi,
                     const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N, const float* __restrict__ mean,
@@ -735,6 +746,30 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
   __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_m1[STRIP_COLS], s_m2[STRIP_COLS];
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * STRIP_COLS;
+  // as in the forward kernel: the thread's first rows are requested before the reductions are finished
+  const int h = t & 1, rr = t >> 1;
+  const int c = c0 + 8 * h;
+  const bool active = c < ld;
+  constexpr int R = X3 ? 2 : STRIP_ROWS_IN_FLIGHT;
+  const int rstep = 128 * static_cast<int>(gridDim.y);
+  const int r_first = rr + 128 * static_cast<int>(blockIdx.y);
+  uint4 dh[R], dl[R], zh[R], zl[R];
+  auto load_batch = [&](int r0) {
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int r = r0 + rstep * u;
+      if (active && r < B) {
+        const size_t o = static_cast<size_t>(r) * ld + c;
+        dh[u] = *reinterpret_cast<const uint4*>(dy_hi + o);
+        zh[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
+        if (X3) {
+          dl[u] = *reinterpret_cast<const uint4*>(dy_lo + o);
+          zl[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
+        }
+      }
+    }
+  };
+  load_batch(r_first);
   {
     const int cl = t & (STRIP_COLS - 1), gl = t >> 4;
     const int c = c0 + cl;
@@ -776,9 +811,7 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
     }
     __syncthreads();
   }
-  const int h = t & 1, rr = t >> 1;
-  const int c = c0 + 8 * h;
-  if (c >= ld) return;
+  if (!active) return;
   float mu[8], rs[8], m1[8], m2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -787,23 +820,8 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
     m1[k] = s_m1[8 * h + k];
     m2[k] = s_m2[8 * h + k];
   }
-  constexpr int R = X3 ? 2 : STRIP_ROWS_IN_FLIGHT;
-  const int rstep = 128 * static_cast<int>(gridDim.y);
-  for (int r0 = rr + 128 * static_cast<int>(blockIdx.y); r0 < B; r0 += rstep * R) {
-    uint4 dh[R], dl[R], zh[R], zl[R];
-#pragma unroll
-    for (int u = 0; u < R; ++u) {
-      const int r = r0 + rstep * u;
-      if (r < B) {
-        const size_t o = static_cast<size_t>(r) * ld + c;
-        dh[u] = *reinterpret_cast<const uint4*>(dy_hi + o);
-        zh[u] = __ldg(reinterpret_cast<const uint4*>(z_hi + o));
-        if (X3) {
-          dl[u] = *reinterpret_cast<const uint4*>(dy_lo + o);
-          zl[u] = __ldg(reinterpret_cast<const uint4*>(z_lo + o));
-        }
-      }
-    }
+  for (int r0 = r_first; r0 < B; r0 += rstep * R) {
+    if (r0 != r_first) load_batch(r0);
 #pragma unroll
     for (int u = 0; u < R; ++u) {
       const int r = r0 + rstep * u;
