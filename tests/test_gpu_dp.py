@@ -52,6 +52,7 @@ def _worker(rank, world, port, out_dir, mode):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["TFK_DP_MODE"] = "" if mode.startswith("fused_step") or mode == "fused" else mode
     os.environ["TFK_DP_RUNAHEAD"] = "0" if mode == "fused_step_unbounded" else "2"
+    os.environ["TFK_DP_OVERLAP"] = "1" if mode.startswith("fused_step") else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     eng = Engine(2, 440, 256, 183, 512, nonlin="linear", precision="bf16x3", device=rank)
@@ -121,7 +122,7 @@ def _c2_shard(rank, step):
     return rng.standard_normal((8192, 440)).astype(np.float32), rng.integers(0, 1936, 8192)
 
 
-def _c2_worker(rank, world, port, out_dir):
+def _c2_worker(rank, world, port, out_dir, overlap):
     import torch
     import torch.distributed as dist
 
@@ -129,6 +130,7 @@ def _c2_worker(rank, world, port, out_dir):
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["TFK_DP_MODE"] = ""
+    os.environ["TFK_DP_OVERLAP"] = "1" if overlap else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     eng = Engine(6, 440, 2048, 1936, 8192, precision="bf16x3", device=rank)
@@ -150,7 +152,8 @@ def _c2_worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(1200)
-def test_dp_full_size_c2_equals_single_gpu_accumulation(cuda_device, tmp_path):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_dp_full_size_c2_equals_single_gpu_accumulation(cuda_device, tmp_path, overlap):
     """configs[2] at full size: K ranks x 8192 frames, 440-6x2048-1936 ReLU net, fp32-equivalent mode, the default
     transport (wgrad epilogues reduce-add into the owners over NVLink, per-layer sharded Adam + operand broadcast under
     the remaining backward pass, flag publish/wait) against ONE GPU accumulating the same K shards as micro-batches
@@ -166,7 +169,7 @@ def test_dp_full_size_c2_equals_single_gpu_accumulation(cuda_device, tmp_path):
     if world < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 1 << (world.bit_length() - 1)  # 2, 4 or 8
-    mp.spawn(_c2_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_c2_worker, args=(world, _free_port(), str(tmp_path), overlap), nprocs=world, join=True)
     single = Engine(6, 440, 2048, 1936, 8192, precision="bf16x3", device=0)
     single.load_params(_c2_params())
     losses = []
@@ -188,5 +191,5 @@ def test_dp_full_size_c2_equals_single_gpu_accumulation(cuda_device, tmp_path):
         for k, v in want.items():
             mine = first[k].astype(np.float64)
             assert other[k][0] == mine.sum() and other[k][1] == np.abs(first[k]).astype(np.float64).sum(), (r, k)
-    print("full-size data parallel, world %d: losses %s, max parameter difference vs single-GPU accumulation after 2 steps %.3e"
-          % (world, losses, worst))
+    print("full-size data parallel, world %d, %s schedule: losses %s, max parameter difference vs single-GPU accumulation after 2 steps %.3e"
+          % (world, "overlapped" if overlap else "serial", losses, worst))

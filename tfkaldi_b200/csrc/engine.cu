@@ -1462,14 +1462,17 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
 }
 
 // Data parallel: the overlapped step needs the fused transports on every layer in use (peer memory on one node,
-// TFK_DP_MODE unset); anything else takes tfk_accumulate + tfk_apply.  TFK_DP_OVERLAP=0 forces the plain sequence.
+// TFK_DP_MODE unset); anything else takes tfk_accumulate + tfk_apply.  It is OPT-IN (TFK_DP_OVERLAP=1): measured at two
+// GPUs (profiles/r2dp_bench_2gpu_*.json) the serial schedule is faster, 1.18 vs 1.28 ms/step — with half of every layer
+// to update per rank the side-stream Adam + peer stores cost the backward GEMMs more (62 us) than the tail they hide;
+// the trade reverses only when the per-rank slices are small and the NVLink-bound tail is long (8 ranks).
 static bool dp_overlap_ready(const tfk_handle* h) {
   if (!(h->sharded && h->fused_rs && h->fused_ag)) return false;
-  static const bool off = [] {
+  static const bool on = [] {
     const char* e = getenv("TFK_DP_OVERLAP");
-    return e && e[0] == '0';
+    return e && e[0] == '1';
   }();
-  if (off) return false;
+  if (!on) return false;
   for (int l = 0; l <= h->L; ++l) {
     if (l < h->L && l >= h->active) continue;
     if (!h->layers[l].peer_reduce) return false;

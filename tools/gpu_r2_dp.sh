@@ -18,14 +18,14 @@ except Exception as e:
     print("no json", e)
 PY
 }
-run overlap TFK_X=1
+run overlap TFK_DP_OVERLAP=1
 run serial TFK_DP_OVERLAP=0
 if [ "$N" = "8" ]; then
   run allreduce TFK_DP_MODE=allreduce
-  run overlap_again TFK_X=1
+  run overlap_again TFK_DP_OVERLAP=1
   run serial_again TFK_DP_OVERLAP=0
 else
-  run overlap_unbounded TFK_DP_RUNAHEAD=0
+  run overlap_unbounded TFK_DP_OVERLAP=1 TFK_DP_RUNAHEAD=0
   run serial_unbounded TFK_DP_OVERLAP=0 TFK_DP_RUNAHEAD=0
 fi
 echo "== bench --gpus 1 (same box)"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity-mode > gpurun_out/bench_1gpu_${TAG}.json 2>/dev/null; python - <<PY
