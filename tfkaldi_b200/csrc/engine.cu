@@ -116,6 +116,7 @@ struct tfk_handle {
   std::vector<__nv_bfloat16*> peer_Sh, peer_Sl;  // every rank's bf16 operand arenas
   int* dp_flags = nullptr;                        // [TFK_DP_FLAG_WORDS] published epochs [slot][source rank] (peers write here)
   int** d_peer_flags = nullptr;                   // device array [nranks-1] of the OTHER ranks' flag arrays
+  int xchg_stride = 0;                            // floats per rank slot of the exchange area behind the flag words
   bool fused_ag = false;                          // Adam stores the refreshed operands into every peer (no NCCL all-gather)
   int dp_epoch = 0;
   std::vector<void*> ipc_opened;
@@ -966,7 +967,9 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
   CREATE_TRY(dev_alloc(h, &h->bn_counters, 512));
   CREATE_TRY(dev_alloc(h, &h->tmp_f32, static_cast<size_t>(maxB) * h->ldmax));
   CREATE_TRY(dev_alloc(h, &h->sched, 2));
-  CREATE_TRY(dev_alloc(h, &h->dp_flags, TFK_DP_FLAG_WORDS));
+  // flag words + the exchange area of the hand-rolled small-vector all-reduce (16 rank slots), one IPC-exported allocation
+  h->xchg_stride = (static_cast<int>(h->arena_n - h->nW) + 4 + 3) / 4 * 4;
+  CREATE_TRY(dev_alloc(h, &h->dp_flags, TFK_DP_FLAG_WORDS + 16 * static_cast<size_t>(h->xchg_stride)));
   {
     cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->acc_host), 2 * sizeof(double));
     if (e != cudaSuccess) return bail(fail(h, TFK_ECUDA, "cudaMallocHost: %s", cudaGetErrorString(e)));
@@ -1264,7 +1267,26 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TFK_CUDA(h, cudaSetDevice(h->cfg.device));
   h->pending_accumulates = 0;
-  if (h->sharded) TFK_TRY(reduce_scatter_grads(h, st));
+  // Fused transports on every layer: nothing is left for NCCL but the small replicated vectors and {loss, frames} —
+  // those go over peer memory too (push into every GPU's exchange slot, flags, rank-ordered sum: ~15 us against the
+  // 35-60 us of a latency-bound NCCL all-reduce on the step's tail).  The flag wait doubles as the barrier that makes
+  // every peer's remote reduce-adds into this rank's accumulators complete before Adam reads them.
+  bool all_fused = h->sharded && h->fused_rs && h->fused_ag && h->nranks <= 16;
+  for (int l = 0; l <= h->L && all_fused; ++l) all_fused = h->layers[l].peer_reduce;
+  static const bool nccl_small = [] {  // TFK_DP_SMALL=nccl keeps the NCCL all-reduce (A/B measurements)
+    const char* e = getenv("TFK_DP_SMALL");
+    return e && strcmp(e, "nccl") == 0;
+  }();
+  const bool peer_small = all_fused && !nccl_small;
+  if (peer_small) {
+    TimerScope ts(h, st, TFK_TIMER_ALLREDUCE, 4);
+    h->dp_epoch += 1;
+    const int small_n = static_cast<int>(h->arena_n - h->nW);
+    TFK_LAUNCH(h, k_dp_small_push(h->d_peer_flags, h->nranks - 1, h->dp_flags, h->rank, h->G + h->nW, h->acc, small_n, h->xchg_stride, st));
+    TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, TFK_DP_FLAG_SLOTS - 1, h->rank, h->dp_epoch, st));
+    TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, TFK_DP_FLAG_SLOTS - 1, h->rank, h->dp_epoch, st));
+    TFK_LAUNCH(h, k_dp_small_reduce(h->dp_flags, h->nranks, h->G + h->nW, h->acc, small_n, h->xchg_stride, st));
+  } else if (h->sharded) TFK_TRY(reduce_scatter_grads(h, st));
   else TFK_TRY(allreduce_grads(h, st));
   h->global_step += 1;  // apply_gradients(global_step=...)   trainer.py:182-184
   h->adam_step += 1;    // beta1_power / beta2_power advance with every apply, whatever global_step is restored to
@@ -1307,7 +1329,7 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
     if (h->fused_ag) {
       // every rank has stored its refreshed operand slices into all peers: publish, then wait for the others
       TimerScope ts(h, st, TFK_TIMER_ALLREDUCE, 2);
-      h->dp_epoch += 1;
+      if (!peer_small) h->dp_epoch += 1;
       TFK_LAUNCH(h, k_dp_publish(h->d_peer_flags, h->nranks - 1, 0, h->rank, h->dp_epoch, st));
       TFK_LAUNCH(h, k_dp_wait(h->dp_flags, h->nranks, 0, h->rank, h->dp_epoch, st));
     } else {

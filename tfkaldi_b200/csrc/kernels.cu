@@ -1208,6 +1208,60 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
   return static_cast<int>(cudaGetLastError());
 }
 
+// Hand-rolled all-reduce of the small replicated vectors (bias / beta gradients) and {loss, frames} over peer memory:
+// every rank stores its copy into slot `me` of the exchange area behind every GPU's flag words (its own included),
+// publishes, waits for the others, and every rank then adds the n slots in RANK ORDER — identical sums everywhere.
+__global__ void __launch_bounds__(256)
+dp_small_push_kernel(int* const* __restrict__ peer_flags, int n_peers, int* __restrict__ own_flags, int flag_words, int me,
+                     const float4* __restrict__ g_small, const double* __restrict__ acc, int small_n4, int stride) {
+  int* base = static_cast<int>(blockIdx.y) < n_peers ? peer_flags[blockIdx.y] : own_flags;
+  float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(base + flag_words) + static_cast<size_t>(me) * stride);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < small_n4; i += gridDim.x * blockDim.x) dst[i] = g_small[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double2 a = make_double2(acc[0], acc[1]);
+    *reinterpret_cast<double2*>(dst + small_n4) = a;  // (stride keeps this 16-byte aligned)
+  }
+  __threadfence_system();
+}
+__global__ void __launch_bounds__(256)
+dp_small_reduce_kernel(const int* __restrict__ own_flags, int flag_words, int n_ranks, float4* __restrict__ g_small,
+                       double* __restrict__ acc, int small_n4, int stride) {
+  const float* x = reinterpret_cast<const float*>(own_flags + flag_words);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < small_n4; i += gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < n_ranks; ++r) {  // fixed order
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * stride) + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    g_small[i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double l = 0.0, f = 0.0;
+    for (int r = 0; r < n_ranks; ++r) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * stride) + small_n4));
+      l += v.x;
+      f += v.y;
+    }
+    acc[0] = l;
+    acc[1] = f;
+  }
+}
+int k_dp_small_push(int* const* d_peer_flags, int n_peers, int* own_flags, int me, const float* g_small, const double* acc,
+                    int small_n, int stride, cudaStream_t st) {
+  const int n4 = small_n >> 2;
+  dim3 grid((n4 + 255) / 256 > 16 ? 16 : ((n4 + 255) / 256 < 1 ? 1 : (n4 + 255) / 256), n_peers + 1);
+  dp_small_push_kernel<<<grid, 256, 0, st>>>(d_peer_flags, n_peers, own_flags, TFK_DP_FLAG_WORDS, me,
+                                             reinterpret_cast<const float4*>(g_small), acc, n4, stride);
+  return static_cast<int>(cudaGetLastError());
+}
+int k_dp_small_reduce(const int* own_flags, int n_ranks, float* g_small, double* acc, int small_n, int stride, cudaStream_t st) {
+  const int n4 = small_n >> 2;
+  int blocks = (n4 + 255) / 256;
+  blocks = blocks > 64 ? 64 : (blocks < 1 ? 1 : blocks);
+  dp_small_reduce_kernel<<<blocks, 256, 0, st>>>(own_flags, TFK_DP_FLAG_WORDS, n_ranks, reinterpret_cast<float4*>(g_small), acc, n4, stride);
+  return static_cast<int>(cudaGetLastError());
+}
+
 int k_dp_publish(int* const* d_peer_flags, int n_peers, int slot, int me, int value, cudaStream_t st) {
   dp_publish_kernel<<<1, 32, 0, st>>>(d_peer_flags, n_peers, slot, me, value);
   return static_cast<int>(cudaGetLastError());

@@ -68,6 +68,12 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
 // The flag array holds [slot][16 ranks] words (TFK_DP_FLAG_WORDS ints): slot 0 paces whole steps, slot 1 + l layers.
 constexpr int TFK_DP_FLAG_SLOTS = 66;
 constexpr int TFK_DP_FLAG_WORDS = TFK_DP_FLAG_SLOTS * 16;
+// Exchange area behind the flag words (same allocation, so the peers have it mapped): [16 ranks][stride floats].
+// k_dp_small_push stores this rank's small_n floats (a multiple of 4) + {loss, frames} into slot `me` on every GPU;
+// after a publish / wait pair k_dp_small_reduce adds the n slots in rank order into g_small / acc.
+int k_dp_small_push(int* const* d_peer_flags, int n_peers, int* own_flags, int me, const float* g_small, const double* acc,
+                    int small_n, int stride, cudaStream_t st);
+int k_dp_small_reduce(const int* own_flags, int n_ranks, float* g_small, double* acc, int small_n, int stride, cudaStream_t st);
 int k_dp_publish(int* const* d_peer_flags, int n_peers, int slot, int me, int value, cudaStream_t st);
 int k_dp_wait(const int* flags, int n_ranks, int slot, int me, int value, cudaStream_t st);
 

@@ -12,22 +12,17 @@ run() {  # name, env...
   python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_${N}gpu_${name}_${TAG}.json"))
+    d=json.loads([l for l in open("gpurun_out/bench_${N}gpu_${name}_${TAG}.json") if l.startswith("{")][-1])  # (NCCL prints its version banner to stdout first)
     print("$name", "value %.3e" % d["value"], d["timing"]["windows_ms_per_step"], d["timing"]["per_step_ms_in_an_extra_window"], "e2e", d["e2e"]["windows_ms_per_step"], d["roofline"]["per_step_us_by_kernel_class"])
 except Exception as e:
     print("no json", e)
 PY
 }
-run overlap TFK_DP_OVERLAP=1
-run serial TFK_DP_OVERLAP=0
-if [ "$N" = "8" ]; then
-  run allreduce TFK_DP_MODE=allreduce
-  run overlap_again TFK_DP_OVERLAP=1
-  run serial_again TFK_DP_OVERLAP=0
-else
-  run overlap_unbounded TFK_DP_OVERLAP=1 TFK_DP_RUNAHEAD=0
-  run serial_unbounded TFK_DP_OVERLAP=0 TFK_DP_RUNAHEAD=0
-fi
+run serial TFK_X=1
+run serial_nccl_small TFK_DP_SMALL=nccl
+run serial_again TFK_X=1
+run serial_nccl_small_again TFK_DP_SMALL=nccl
+if [ "$N" != "2" ]; then run allreduce TFK_DP_MODE=allreduce; fi
 echo "== bench --gpus 1 (same box)"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity-mode > gpurun_out/bench_1gpu_${TAG}.json 2>/dev/null; python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_1gpu_${TAG}.json")); print("1gpu value %.3e" % d["value"], d["timing"]["windows_ms_per_step"])
