@@ -901,7 +901,7 @@ int tfk_create(const tfk_config* cfg, tfk_handle** out) {
     ly.off_b = off; off += ly.npad;
     if (ly.bn) { ly.off_beta = off; off += ly.npad; }
   }
-  h->arena_n = (off + 3) / 4 * 4;
+  h->arena_n = (off + 7) / 8 * 8;  // the Adam kernel works on 8-float granules
   h->ld0 = h->layers[0].ldk;
   h->ldh = round_up(cfg->hidden_dim, 8);
   h->ldo = round_up(cfg->output_dim, 8);

@@ -362,8 +362,8 @@ struct AdamSegs {
   // fused update -> all-gather: the refreshed bf16 operand copies of the first `n_bcast` segments are also
   // stored into every peer GPU's shadow arena over NVLink (peer_hi[r] / peer_lo[r], r != self)
   int n_bcast, n_peers;
-  uint2* peer_hi[15];
-  uint2* peer_lo[15];
+  uint4* peer_hi[15];
+  uint4* peer_lo[15];
 };
 // blockIdx.y = segment (the whole arena on one GPU; a rank's slice of every layer + the small
 // replicated region under sharded data parallelism)
@@ -372,35 +372,44 @@ struct AdamSegs {
 // per-layer updates launched on the side stream really run under the backward kernels instead of in the gaps between them.
 __global__ void __launch_bounds__(128)
 adam_kernel(float4* __restrict__ w, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-            uint2* __restrict__ w_hi, uint2* __restrict__ w_lo, const AdamSegs segs, const double* __restrict__ acc,
+            uint4* __restrict__ w_hi, uint4* __restrict__ w_lo, const AdamSegs segs, const double* __restrict__ acc,
             float lr_t, float b1, float b2, float eps) {
   const float frames = static_cast<float>(acc[1]);
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-  const size_t base = segs.off4[blockIdx.y], n4 = segs.cnt4[blockIdx.y];
-  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n4;
+  // eight parameters per thread and iteration: eight independent 16-byte loads in flight, and the refreshed bf16
+  // operands leave as ONE 16-byte store per destination (the peer copies travel over NVLink: half as many packets as
+  // with 8-byte stores)
+  const size_t base = segs.off4[blockIdx.y] >> 1, n8 = segs.cnt4[blockIdx.y] >> 1;
+  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n8;
        k += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t i = base + k;
-    const float4 gg = g[i];
-    float4 mm = m[i], vv = v[i], ww = w[i];
-    float gx[4] = {gg.x, gg.y, gg.z, gg.w};
-    float mx[4] = {mm.x, mm.y, mm.z, mm.w};
-    float vx[4] = {vv.x, vv.y, vv.z, vv.w};
-    float wx[4] = {ww.x, ww.y, ww.z, ww.w};
+    const float4 g0 = g[2 * i], g1 = g[2 * i + 1], m0 = m[2 * i], m1 = m[2 * i + 1];
+    const float4 v0 = v[2 * i], v1 = v[2 * i + 1], w0 = w[2 * i], w1 = w[2 * i + 1];
+    float gx[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float mx[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vx[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float wx[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int k2 = 0; k2 < 4; ++k2) {
+    for (int k2 = 0; k2 < 8; ++k2) {
       float gh = gx[k2] / frames;                      // tf.div(grad, num_frames)   trainer.py:174
       gh = fminf(fmaxf(gh, -1.0f), 1.0f);              // tf.clip_by_value(-1, 1)    trainer.py:178
       mx[k2] += (gh - mx[k2]) * omb1;                  // TF ApplyAdam
       vx[k2] += (gh * gh - vx[k2]) * omb2;
       wx[k2] -= (mx[k2] * lr_t) / (sqrtf(vx[k2]) + eps);
     }
-    m[i] = make_float4(mx[0], mx[1], mx[2], mx[3]);
-    v[i] = make_float4(vx[0], vx[1], vx[2], vx[3]);
-    w[i] = make_float4(wx[0], wx[1], wx[2], wx[3]);
-    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);            // init_grads                 trainer.py:350
-    uint2 h, l;
+    m[2 * i] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+    m[2 * i + 1] = make_float4(mx[4], mx[5], mx[6], mx[7]);
+    v[2 * i] = make_float4(vx[0], vx[1], vx[2], vx[3]);
+    v[2 * i + 1] = make_float4(vx[4], vx[5], vx[6], vx[7]);
+    w[2 * i] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+    w[2 * i + 1] = make_float4(wx[4], wx[5], wx[6], wx[7]);
+    g[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);        // init_grads                 trainer.py:350
+    g[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 h, l;
     split2(wx[0], wx[1], h.x, l.x);
     split2(wx[2], wx[3], h.y, l.y);
+    split2(wx[4], wx[5], h.z, l.z);
+    split2(wx[6], wx[7], h.w, l.w);
     w_hi[i] = h;
     if (w_lo) w_lo[i] = l;
     if (static_cast<int>(blockIdx.y) < segs.n_bcast) {
@@ -1187,11 +1196,12 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
     segs.n_peers = segs.n_bcast > 0 ? n_peers : 0;
     if (segs.n_peers > 15) return static_cast<int>(cudaErrorInvalidValue);
     for (int r = 0; r < segs.n_peers; ++r) {
-      segs.peer_hi[r] = reinterpret_cast<uint2*>(peer_hi[r]);
-      segs.peer_lo[r] = peer_lo ? reinterpret_cast<uint2*>(peer_lo[r]) : nullptr;
+      segs.peer_hi[r] = reinterpret_cast<uint4*>(peer_hi[r]);
+      segs.peer_lo[r] = peer_lo ? reinterpret_cast<uint4*>(peer_lo[r]) : nullptr;
     }
     size_t longest = 0;
     for (int i = 0; i < segs.n; ++i) {
+      if ((seg_off[s0 + i] | seg_cnt[s0 + i]) & 7) return static_cast<int>(cudaErrorInvalidValue);  // 8-float granules
       segs.off4[i] = seg_off[s0 + i] >> 2;
       segs.cnt4[i] = seg_cnt[s0 + i] >> 2;
       longest = segs.cnt4[i] > longest ? segs.cnt4[i] : longest;
@@ -1199,10 +1209,10 @@ int k_adam(float* w, float* g, float* m, float* v, __nv_bfloat16* w_hi, __nv_bfl
     if (longest == 0) continue;
     int per_seg = 148 * 16 / segs.n;
     if (per_seg < 16) per_seg = 16;
-    dim3 grid(grid_for(longest, 128, per_seg), segs.n);
+    dim3 grid(grid_for(longest >> 1, 128, per_seg), segs.n);
     adam_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(g),
                                       reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
-                                      reinterpret_cast<uint2*>(w_hi), reinterpret_cast<uint2*>(w_lo), segs, acc, lr_t,
+                                      reinterpret_cast<uint4*>(w_hi), reinterpret_cast<uint4*>(w_lo), segs, acc, lr_t,
                                       beta1, beta2, eps);
   }
   return static_cast<int>(cudaGetLastError());
