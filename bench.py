@@ -348,12 +348,17 @@ def run_ours(args):
 
 def _ncu_traffic(args, frames):
     """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this exact
-    workload (profiles/r1_ncu_traffic.json); null for workloads that were not captured."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_traffic.json")
-    try:
-        t = json.load(open(path)).get("%s:%s:%d" % (args.config, args.precision, frames))
-    except (OSError, ValueError):
-        t = None
+    workload (profiles/r2_ncu_traffic.json from the last build's capture, tools/ncu_traffic.py; else the round-1 file);
+    null for workloads that were not captured."""
+    t = None
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", name)
+        try:
+            t = json.load(open(path)).get("%s:%s:%d" % (args.config, args.precision, frames))
+        except (OSError, ValueError):
+            t = None
+        if t:
+            break
     if not t:
         return {"traffic": None}
     return {"traffic": t["dram_bytes_per_launch"], "traffic_unit": "bytes of DRAM read+write per launch (mean of the %d launches of a step)" % t["launches_per_step"],
