@@ -159,6 +159,11 @@ int tfk_forward_loglik_raw_rows(tfk_handle* h, const float* raw, const int32_t* 
  * learning_rate_fact.  mean_loss_host (may be NULL => no host sync) receives batch_loss/num_frames
  * evaluated with the pre-update weights. */
 int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream);
+/* The mean loss of the most recent tfk_apply / tfk_train_step / tfk_train_step_raw that was called with
+ * mean_loss_host == NULL: waits for that step and returns batch_loss/num_frames exactly as the step itself would have.
+ * It lets the caller put host work (queueing the next batch's copy, trainer.py's logging) between launching a step
+ * and blocking on its loss.  TFK_EINVAL when no such step is outstanding. */
+int tfk_last_loss(tfk_handle* h, float* mean_loss_host, void* stream);
 
 /* == tfk_accumulate + tfk_apply for ONE micro-batch (the reference's update() with
  * numutterances_per_minibatch covering the whole batch, trainer.py:310-352), same arithmetic; on a single

@@ -93,7 +93,14 @@ class OracleEngine(object):
     def apply(self, lr, want_loss=True):
         self.calls.append("apply")
         loss = self.orc.apply(lr)
+        self._pending_loss = None if want_loss else float(loss)
         return float(loss) if want_loss else None
+
+    def last_loss(self):
+        if getattr(self, "_pending_loss", None) is None:
+            raise L.TfkError(L.TFK_EINVAL, "tfk_last_loss: no step with an unread loss is outstanding")
+        loss, self._pending_loss = self._pending_loss, None
+        return loss
 
     def train_step(self, x, labels, lr, want_loss=True):
         self.calls.append("train_step")

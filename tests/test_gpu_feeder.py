@@ -86,3 +86,25 @@ def test_feeder_path_agrees_with_the_host_spliced_path(cuda_device, tmp_path):
         lb = b.update_prefetched(feeder)
         assert abs(la - lb) <= 1e-4 * max(1.0, abs(la)), (step, la, lb)
     feeder.close()
+
+
+def test_update_packed_with_prefetch_equals_without(cuda_device, tmp_path):
+    """update_packed(prefetch=next batch) launches the step, queues the next batch's copy and only then reads the loss
+    (tfk_last_loss): identical losses and parameters to feeding the same pinned batches one at a time."""
+    import torch
+
+    _, trainer = build(tmp_path, 4, 4)
+    a, b = trainer(), trainer()
+    rng = np.random.default_rng(3)
+    xs = [torch.from_numpy(rng.standard_normal((200 + 8 * i, 440)).astype(np.float32)).pin_memory() for i in range(5)]
+    ys = [torch.from_numpy(rng.integers(0, 183, x.shape[0]).astype(np.int32)).pin_memory() for x in xs]
+    b.prefetch(xs[0], ys[0])
+    for i in range(5):
+        a.engine.set_dropout_seed(900 + 10 * i)
+        b.engine.set_dropout_seed(900 + 10 * i)
+        la = a.update_packed(xs[i], ys[i])
+        lb = b.update_packed(xs[i], ys[i], prefetch=(xs[i + 1], ys[i + 1]) if i < 4 else None)
+        assert la == lb, i
+    pa, pb = a.engine.dump_params(), b.engine.dump_params()
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), k

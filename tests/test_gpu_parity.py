@@ -417,3 +417,32 @@ def test_fused_train_step_equals_accumulate_plus_apply(cuda_device, variant):
     a.accumulate(x2, y2); a.accumulate(x, y); la = a.apply(1e-3)
     b.accumulate(x2, y2); lb = b.train_step(x, y, 1e-3)  # open accumulation -> sequential path, two micro-batches
     assert la == lb and np.array_equal(a.dump_params()["W1"], b.dump_params()["W1"])
+
+
+def test_last_loss_is_the_deferred_loss_of_the_step(cuda_device):
+    """tfk_last_loss: a step launched without a loss pointer hands the same mean loss out afterwards (both through
+    tfk_train_step and tfk_accumulate + tfk_apply), once; asking again, or before any step, is an error."""
+    from tfkaldi_b200 import _lib as L
+
+    cfg = OracleConfig(**{**C1, **VARIANTS["plain"]})
+    _, a, rng = make_pair(cfg, 256, "bf16", seed=9, random_out=True)
+    _, b, _ = make_pair(cfg, 256, "bf16", seed=9, random_out=True)
+    with pytest.raises(L.TfkError):
+        b.last_loss()
+    for step in range(3):
+        x = rng.standard_normal((256, 440)).astype(np.float32)
+        y = rng.integers(0, 183, 256)
+        la = a.train_step(x, y, 2e-3)
+        if step == 1:
+            b.accumulate(x, y)
+            assert b.apply(2e-3, want_loss=False) is None
+        else:
+            assert b.train_step(x, y, 2e-3, want_loss=False) is None
+        assert b.last_loss() == la
+        with pytest.raises(L.TfkError):
+            b.last_loss()
+    assert np.array_equal(a.dump_params()["W1"], b.dump_params()["W1"])
+    lb = b.train_step(x, y, 2e-3)  # a step that returns its loss leaves nothing outstanding
+    assert math.isfinite(lb)
+    with pytest.raises(L.TfkError):
+        b.last_loss()

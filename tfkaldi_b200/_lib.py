@@ -68,6 +68,7 @@ SIGNATURES = [
     ("tfk_forward_loglik_raw", C.c_int, [_H, _FP, _FP, C.c_int, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, C.c_void_p]),
     ("tfk_forward_loglik_raw_rows", C.c_int, [_H, _FP, _FP, C.c_int, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _FP, _FP, C.c_void_p]),
     ("tfk_apply", C.c_int, [_H, C.c_float, C.POINTER(C.c_float), C.c_void_p]),
+    ("tfk_last_loss", C.c_int, [_H, C.POINTER(C.c_float), C.c_void_p]),
     ("tfk_train_step", C.c_int, [_H, _FP, _FP, C.c_int, C.c_float, C.POINTER(C.c_float), C.c_void_p]),
     ("tfk_train_step_raw", C.c_int, [_H, _FP, _FP, C.c_int, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.c_void_p]),
     ("tfk_eval_accumulate", C.c_int, [_H, _FP, _FP, C.c_int, C.c_void_p]),

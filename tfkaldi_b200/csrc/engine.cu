@@ -131,6 +131,7 @@ struct tfk_handle {
   float* row_loss = nullptr;
   double* acc = nullptr;  // device {loss_sum, num_frames}
   double* acc_host = nullptr;
+  bool loss_pending = false;  // a step's {loss, frames} copy into acc_host is queued and has not been read (tfk_last_loss)
   float *bn_ps = nullptr, *bn_pq = nullptr;
   float* ws = nullptr;
   float* ws_colsum = nullptr;
@@ -1035,6 +1036,7 @@ int tfk_get_scalar(tfk_handle* h, int kind, double* value_host, void* stream) {
       cudaStream_t st = static_cast<cudaStream_t>(stream);
       TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
       TFK_CUDA(h, cudaStreamSynchronize(st));
+      h->loss_pending = false;  // acc_host now holds the running sums, not the last step's
       *value_host = h->acc_host[kind == TFK_S_LOSS_SUM ? 0 : 1];
       return TFK_OK;
     }
@@ -1339,12 +1341,22 @@ int tfk_apply(tfk_handle* h, float lr, float* mean_loss_host, void* stream) {
   }
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));  // init_loss / init_num_frames
+  h->loss_pending = mean_loss_host == nullptr;
   if (mean_loss_host) {
     TFK_CUDA(h, cudaStreamSynchronize(st));
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);  // average_loss   trainer.py:198
   } else {
     TFK_TRY(bound_runahead(h, st));
   }
+  return TFK_OK;
+}
+
+int tfk_last_loss(tfk_handle* h, float* mean_loss_host, void* stream) {
+  if (!h || !mean_loss_host) return fail(h, TFK_EINVAL, "tfk_last_loss: null argument");
+  if (!h->loss_pending) return fail(h, TFK_EINVAL, "tfk_last_loss: no step with an unread loss is outstanding");
+  TFK_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
+  h->loss_pending = false;
   return TFK_OK;
 }
 
@@ -1474,6 +1486,7 @@ static int train_step_loaded(tfk_handle* h, Plan* plan, const int32_t* labels, i
   advance_drop_seed(h);
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));
+  h->loss_pending = mean_loss_host == nullptr;
   if (mean_loss_host) {
     TFK_CUDA(h, cudaStreamSynchronize(st));
     *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
@@ -1565,6 +1578,7 @@ int tfk_eval_finish(tfk_handle* h, float* mean_loss_host, void* stream) {
   TFK_CUDA(h, cudaMemcpyAsync(h->acc_host, h->acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFK_CUDA(h, cudaMemsetAsync(h->acc, 0, 2 * sizeof(double), st));
   TFK_CUDA(h, cudaStreamSynchronize(st));
+  h->loss_pending = false;
   *mean_loss_host = static_cast<float>(h->acc_host[0] / h->acc_host[1]);
   return TFK_OK;
 }

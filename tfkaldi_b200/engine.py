@@ -187,6 +187,12 @@ class Engine:
                                                 C.byref(out) if want_loss else None, self._stream()))
         return out.value if want_loss else None
 
+    def last_loss(self):
+        """the mean loss of the last step run with want_loss=False (blocks until that step has finished)"""
+        out = C.c_float()
+        self._check(self.lib.tfk_last_loss(self.h, C.byref(out), self._stream()))
+        return out.value
+
     def eval_accumulate(self, x, labels):
         x, labels = self._dev_f32(x), self._dev_i32(labels)
         self._check(self.lib.tfk_eval_accumulate(self.h, _ptr(x), _ptr(labels), x.shape[0], self._stream()))

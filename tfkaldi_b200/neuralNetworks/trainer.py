@@ -282,13 +282,17 @@ class Trainer(object, metaclass=ABCMeta):
                 if isinstance(x, torch.Tensor):
                     x, y = x.numpy(), y.numpy()
                 k, dx, dy = self._stager.stage(x, y)
-            if prefetch is not None:
-                # queue the next batch's H2D first (copy stream): it overlaps this whole step
-                self.prefetch(*prefetch)
-            # one micro-batch: fused step (per-layer Adam overlapped with the backward pass on one GPU)
-            loss = self.engine.train_step(dx, dy, self.learning_rate_cached(), want_loss)
+            # one micro-batch: fused step (per-layer Adam overlapped with the backward pass on one GPU).  The step is
+            # launched first; the next batch's H2D is queued (copy stream) while it runs, then the host blocks on the loss
+            lr = self.learning_rate_cached()
+            if prefetch is None:
+                loss = self.engine.train_step(dx, dy, lr, want_loss)
+                self._stager.release(k)
+                return self._log(loss)
+            self.engine.train_step(dx, dy, lr, False)
             self._stager.release(k)
-            return self._log(loss)
+            self.prefetch(*prefetch)
+            return self._log(self.engine.last_loss() if want_loss else None)
 
     def update_raw(self, raw_utts, cmvn_stats, targets, context_width):
         """update() from RAW features: list of un-normalised [T_u, D] matrices, their speakers' CMVN
@@ -320,13 +324,17 @@ class Trainer(object, metaclass=ABCMeta):
         parts = list(batch.microbatches())
         if len(parts) == 1:
             raw, labels, offsets, cmvn = parts[0]
-            loss = self.engine.train_step_raw(raw, offsets, cmvn, labels, batch.feat_dim, context, lr, True)
+            # launch the step, do the host work of the NEXT batch while it runs, only then block on the loss
+            self.engine.train_step_raw(raw, offsets, cmvn, labels, batch.feat_dim, context, lr, False)
             feeder.consumed(batch)
-            return self._log(loss)
+            feeder.stage_next()
+            return self._log(self.engine.last_loss())
         for raw, labels, offsets, cmvn in parts:
             self.engine.accumulate_raw(raw, offsets, cmvn, labels, batch.feat_dim, context)
         feeder.consumed(batch)
-        return self._apply()
+        self.engine.apply(self.learning_rate_cached(), False)
+        feeder.stage_next()
+        return self._log(self.engine.last_loss())
 
     def _apply(self, want_loss=True):
         return self._log(self.engine.apply(self.learning_rate_cached(), want_loss))

@@ -264,8 +264,8 @@ class RawBatchFeeder(object):
         return batch
 
     def get_on_device(self, device=None):
-        """the next batch with its device views; the compute stream is made to wait for the copy.  If the batch after
-        it is already packed, its copy is queued right away so that it overlaps the step about to run."""
+        """the next batch with its device views; the compute stream is made to wait for the copy.  Call
+        `stage_next()` once the step's kernels are queued, so that the next batch's copy is set up while they run."""
         if device is not None and self._dev is None:
             self.device = device
         batch = self._staged if self._staged is not None else self._stage(self.get())
@@ -273,14 +273,21 @@ class RawBatchFeeder(object):
         self.frames_out += batch.frames
         d = self._dev
         torch.cuda.current_stream(d["device"]).wait_event(d["copied"][batch.device_slot])
-        try:  # (only this thread takes batches out of the queue: no lock, the packer may hold it for a whole batch)
+        return batch
+
+    def stage_next(self):
+        """if the batch after the one in flight is already packed, queue its host->device copy now: it overlaps the
+        step that was just launched.  (Only this thread takes batches out of the queue: no lock needed, the packer
+        may hold it for a whole batch.)"""
+        if self._staged is not None:
+            return
+        try:
             nxt = self._ready.get_nowait()
         except queue.Empty:
-            return batch
+            return
         if nxt is None:
             raise RuntimeError("feeder thread failed") from self._error
         self._staged = self._stage(nxt)
-        return batch
 
     def consumed(self, batch):
         """call after the step's kernels have been enqueued: marks the device buffer and recycles the pinned slot"""
