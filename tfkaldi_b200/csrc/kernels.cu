@@ -608,12 +608,22 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat1
 // direction instead of a tiny latency-bound `finalize` launch followed by an `apply` launch (the two finalize kernels
 // were 78 us of a C4 step: profiles/r2b_ncu_full_summary_c4_small_kernels.txt).
 constexpr int STRIP_COLS = 16;
-constexpr int STRIP_ROWS_IN_FLIGHT = 4;
+constexpr int STRIP_ROWS_IN_FLIGHT = 4;       // bf16x3 (hi + lo arrays)
+constexpr int STRIP_ROWS_IN_FLIGHT_BF16 = 6;  // bf16: a thread's 10-11 rows of a C4 strip (4096 rows, 3 row splits) in two batches
+constexpr int STRIP_BLOCKS_PER_SM = 3;
+
+// eight consecutive floats of a 16-byte-aligned shared array; `volatile` keeps the loads where they are written (hoisted
+// out of the row loop they would pin 24-32 registers for the whole kernel)
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a) : "memory");
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a + 16u) : "memory");
+}
 
 // forward: statistics (training: from the partials, with the moving-average update; eval: the moving statistics), then
 // y = f((z - mean) * rstd + beta) [* dropout]   (reference: classifiers/activation.py:159-161 -> nonlinearity -> 140-141)
 template <bool X3>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, STRIP_BLOCKS_PER_SM)
 bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int groups, int pld,
                     const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N,
                     float eps, float decay, int training, float* __restrict__ mean, float* __restrict__ rstd,
@@ -622,7 +632,7 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
                     __nv_bfloat16* __restrict__ y_lo) {
   pdl_enter();
   __shared__ double sm[2][16][STRIP_COLS + 1];
-  __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_be[STRIP_COLS];
+  __shared__ __align__(16) float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_be[STRIP_COLS];
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * STRIP_COLS;
   // streaming role of this thread: 8 of the strip's 16 columns, one row per 128-row sweep.  Its first rows are
@@ -633,11 +643,12 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
   const bool active = c < ld;
   const int rstep = 128 * static_cast<int>(gridDim.y);
   const int r_first = rr + 128 * static_cast<int>(blockIdx.y);
-  uint4 hv[STRIP_ROWS_IN_FLIGHT], lv[STRIP_ROWS_IN_FLIGHT];
-  uint32_t keepb[STRIP_ROWS_IN_FLIGHT];
+  constexpr int RIF = X3 ? STRIP_ROWS_IN_FLIGHT : STRIP_ROWS_IN_FLIGHT_BF16;
+  uint4 hv[RIF], lv[RIF];
+  uint32_t keepb[RIF];
   auto load_batch = [&](int r0) {
 #pragma unroll
-    for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
+    for (int u = 0; u < RIF; ++u) {
       const int r = r0 + rstep * u;
       keepb[u] = 0xFFu;
       if (active && r < B) {
@@ -651,6 +662,15 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
     }
   };
   load_batch(r_first);
+  // the finishing threads' own operands are requested now too, not behind the reduction's barrier
+  float pre_beta = 0.f, pre_mm = 0.f, pre_mv = 1.f;
+  if (t < STRIP_COLS && c0 + t < N) {
+    pre_beta = beta[c0 + t];
+    if (!training || blockIdx.y == 0) {
+      pre_mm = mm[c0 + t];
+      pre_mv = mv[c0 + t];
+    }
+  }
   {
     const int cl = t & (STRIP_COLS - 1), gl = t >> 4;  // 16 columns x 16 group lanes
     const int c = c0 + cl;
@@ -692,18 +712,18 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
           const float varf = static_cast<float>(var);
           rsf = rsqrtf(varf + eps);
           if (blockIdx.y == 0) {  // every row split of a strip derives the same statistics; one of them records them
-            mm[cc] -= (1.0f - decay) * (mm[cc] - muf);  // assign_moving_average
-            mv[cc] -= (1.0f - decay) * (mv[cc] - varf);
+            mm[cc] = pre_mm - (1.0f - decay) * (pre_mm - muf);  // assign_moving_average
+            mv[cc] = pre_mv - (1.0f - decay) * (pre_mv - varf);
           }
         } else {
-          muf = mm[cc];
-          rsf = rsqrtf(mv[cc] + eps);
+          muf = pre_mm;
+          rsf = rsqrtf(pre_mv + eps);
         }
         if (blockIdx.y == 0) {
           mean[cc] = muf;  // kept for the backward pass
           rstd[cc] = rsf;
         }
-        bef = beta[cc];
+        bef = pre_beta;
       }
       s_mu[t] = muf;
       s_rs[t] = rsf;
@@ -712,21 +732,18 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
     __syncthreads();
   }
   if (!active) return;
-  float mu[8], rs[8], be[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    mu[k] = s_mu[8 * h + k];
-    rs[k] = s_rs[8 * h + k];
-    be[k] = s_be[8 * h + k];
-  }
-  for (int r0 = r_first; r0 < B; r0 += rstep * STRIP_ROWS_IN_FLIGHT) {
+  for (int r0 = r_first; r0 < B; r0 += rstep * RIF) {
     if (r0 != r_first) load_batch(r0);
 #pragma unroll
-    for (int u = 0; u < STRIP_ROWS_IN_FLIGHT; ++u) {
+    for (int u = 0; u < RIF; ++u) {
       const int r = r0 + rstep * u;
       if (r >= B) continue;
-      float x[8];
+      float x[8], mu[8], rs[8], be[8];
       unpack8(hv[u], lv[u], X3, x);
+      // the strip's constants are re-read from shared memory per row: registers go to rows in flight instead
+      lds8(s_mu + 8 * h, mu);
+      lds8(s_rs + 8 * h, rs);
+      lds8(s_be + 8 * h, be);
       const uint32_t keep = keepb[u];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -745,21 +762,21 @@ bn_fwd_strip_kernel(const float* __restrict__ ps, const float* __restrict__ pq, 
 // backward: m1 = mean_B(dy), m2 = mean_B(dy * xhat) from the dgrad epilogue's partials (and dbeta += sum_B dy), then
 // dz = rstd * (dy - m1 - xhat * m2) in place over dy
 template <bool X3>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, STRIP_BLOCKS_PER_SM)
 bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int groups, int pld,
                     __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo, const __nv_bfloat16* __restrict__ z_hi,
                     const __nv_bfloat16* __restrict__ z_lo, int ld, int B, int N, const float* __restrict__ mean,
                     const float* __restrict__ rstd, float* __restrict__ g_beta) {
   pdl_enter();
   __shared__ float sm[2][16][STRIP_COLS + 1];
-  __shared__ float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_m1[STRIP_COLS], s_m2[STRIP_COLS];
+  __shared__ __align__(16) float s_mu[STRIP_COLS], s_rs[STRIP_COLS], s_m1[STRIP_COLS], s_m2[STRIP_COLS];
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * STRIP_COLS;
   // as in the forward kernel: the thread's first rows are requested before the reductions are finished
   const int h = t & 1, rr = t >> 1;
   const int c = c0 + 8 * h;
   const bool active = c < ld;
-  constexpr int R = X3 ? 2 : STRIP_ROWS_IN_FLIGHT;
+  constexpr int R = X3 ? 2 : STRIP_ROWS_IN_FLIGHT_BF16;  // (two arrays per row)
   const int rstep = 128 * static_cast<int>(gridDim.y);
   const int r_first = rr + 128 * static_cast<int>(blockIdx.y);
   uint4 dh[R], dl[R], zh[R], zl[R];
@@ -779,6 +796,12 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
     }
   };
   load_batch(r_first);
+  float pre_mu = 0.f, pre_rs = 0.f, pre_gb = 0.f;  // the finishing threads' operands: requested before the reduction
+  if (t < STRIP_COLS && c0 + t < N) {
+    pre_mu = mean[c0 + t];
+    pre_rs = rstd[c0 + t];
+    if (blockIdx.y == 0) pre_gb = g_beta[c0 + t];
+  }
   {
     const int cl = t & (STRIP_COLS - 1), gl = t >> 4;
     const int c = c0 + cl;
@@ -811,33 +834,29 @@ bn_bwd_strip_kernel(const float* __restrict__ p1, const float* __restrict__ p2, 
         t2 += sm[1][k][t];
       }
       const bool ok = cc < N;
-      if (ok && blockIdx.y == 0) g_beta[cc] += t1;
+      if (ok && blockIdx.y == 0) g_beta[cc] = pre_gb + t1;
       const float invB = 1.0f / static_cast<float>(B);
       s_m1[t] = ok ? t1 * invB : 0.f;
       s_m2[t] = ok ? t2 * invB : 0.f;
-      s_mu[t] = ok ? mean[cc] : 0.f;
-      s_rs[t] = ok ? rstd[cc] : 0.f;
+      s_mu[t] = pre_mu;
+      s_rs[t] = pre_rs;
     }
     __syncthreads();
   }
   if (!active) return;
-  float mu[8], rs[8], m1[8], m2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    mu[k] = s_mu[8 * h + k];
-    rs[k] = s_rs[8 * h + k];
-    m1[k] = s_m1[8 * h + k];
-    m2[k] = s_m2[8 * h + k];
-  }
   for (int r0 = r_first; r0 < B; r0 += rstep * R) {
     if (r0 != r_first) load_batch(r0);
 #pragma unroll
     for (int u = 0; u < R; ++u) {
       const int r = r0 + rstep * u;
       if (r >= B) continue;
-      float d[8], z[8];
+      float d[8], z[8], mu[8], rs[8], m1[8], m2[8];
       unpack8(dh[u], dl[u], X3, d);
       unpack8(zh[u], zl[u], X3, z);
+      lds8(s_mu + 8 * h, mu);
+      lds8(s_rs + 8 * h, rs);
+      lds8(s_m1 + 8 * h, m1);
+      lds8(s_m2 + 8 * h, m2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float xh = (z[k] - mu[k]) * rs[k];
@@ -1295,11 +1314,13 @@ int k_bn_bwd_reduce(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, cons
                                                       sums, g_beta);
   return static_cast<int>(cudaGetLastError());
 }
-// strips x row splits: about four 256-thread blocks per SM (every row split re-derives its strip's statistics from the
-// same partials: a few KB from L2, identical results)
+// strips x row splits (every row split re-derives its strip's statistics from the same partials: a few KB from L2,
+// identical results)
 static dim3 strip_grid(int ld, int B) {
   const int strips = (ld + STRIP_COLS - 1) / STRIP_COLS;
-  int rs = (148 * 4 + strips - 1) / strips;
+  // ONE wave of resident blocks: these kernels are latency chains (reduce the statistics, then one or two batches of rows),
+  // so a partly filled second wave costs a whole chain more (640 blocks on 444 slots: 18 us per launch)
+  int rs = 148 * STRIP_BLOCKS_PER_SM / strips;
   const int max_rs = (B + 127) / 128;
   if (rs > max_rs) rs = max_rs;
   if (rs < 1) rs = 1;
