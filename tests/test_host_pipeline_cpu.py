@@ -308,3 +308,70 @@ def test_adam_step_count_survives_restore_and_restarts_on_initialize(host_only, 
     full.restore_trainer(str(tmp_path / "step5"), restore_optimizer=True)
     assert full.engine.get_scalar(L.S_ADAM_STEP) == 5 and full.engine.get_tensor(L.T_ADAM_V_W, 2).any()
     del w_before
+
+
+@pytest.mark.parametrize("n", [8, 4])
+def test_update_prefetched_defers_the_loss_read_behind_the_next_batchs_staging(host_only, tmp_path, n):
+    """Trainer.update_prefetched: the step is launched WITHOUT a loss pointer, the slot is recycled and the next batch
+    staged, and only then the loss is read (tfk_last_loss) — with the loss and the weights of the synchronous raw path
+    (Trainer.update_raw), for one micro-batch per step (tfk_train_step_raw) and for two (accumulate_raw x 2 + apply)."""
+    from tfkaldi_b200.neuralNetworks.classifiers import activation as act
+    from tfkaldi_b200.neuralNetworks.classifiers.dnn import DNN
+    from tfkaldi_b200.neuralNetworks.trainer import CrossEnthropyTrainer
+    from tfkaldi_b200.processing.feeder import RawBatchFeeder
+
+    events = []
+
+    class HostFeeder(RawBatchFeeder):  # the device half replaced: host tensors stand for the device views
+        def get_on_device(self, device=None):
+            batch = self._staged if self._staged is not None else self.get()
+            self._staged = None
+            return batch
+
+        def stage_next(self):
+            events.append("stage_next")
+            if self._staged is None:
+                self._staged = self.get()
+
+        def consumed(self, batch):
+            events.append("consumed")
+            self._free.put(batch.slot)
+
+    for name in ("train_step", "train_step_raw", "apply", "last_loss"):
+        def wrap(self, *a, _f=getattr(OracleEngine, name), _n=name, **kw):
+            events.append((_n, a[-1] if _n != "last_loss" else None))  # (call, want_loss)
+            return _f(self, *a, **kw)
+        setattr(host_only, "_orig_" + name, getattr(OracleEngine, name))
+        setattr(host_only, name, wrap)
+    try:
+        da, _, _ = corpora(tmp_path)
+        db, _, _ = corpora(tmp_path)
+
+        def trainer():
+            dnn = DNN(60, 2, 64, act.TfActivation(None, act.relu), False)
+            tr = CrossEnthropyTrainer(dnn, 440, da.max_input_length, da.max_input_length, 1e-3, 1.0, 1000, n)
+            tr.initialize()
+            tr.engine.set_tensor(L.T_WEIGHTS, 2, (np.random.default_rng(5).standard_normal((64, 60)) / 8).astype(np.float32))
+            return tr
+
+        a, b = trainer(), trainer()
+        feeder = HostFeeder(db, n)
+        for step in range(3):
+            la = a.update_raw(*da.get_raw_batch(), 5)
+            del events[:]
+            lb = b.update_prefetched(feeder)
+            assert lb == la, step
+            if n == 8:  # one micro-batch: the fused step (the stand-in's train_step_raw = train_step = accumulate + apply)
+                want = [("train_step_raw", False), ("train_step", False), ("apply", False), "consumed"]
+            else:  # two micro-batches: the batch's data has been consumed once both accumulates are queued
+                want = ["consumed", ("apply", False)]
+            assert events == want + ["stage_next", ("last_loss", None)], events
+        feeder.close()
+        for k, v in a.engine.dump_params().items():
+            assert np.array_equal(v, b.engine.dump_params()[k]), k
+        with pytest.raises(L.TfkError):
+            b.engine.last_loss()  # read once
+    finally:
+        for name in ("train_step", "train_step_raw", "apply", "last_loss"):
+            setattr(host_only, name, getattr(host_only, "_orig_" + name))
+            delattr(host_only, "_orig_" + name)

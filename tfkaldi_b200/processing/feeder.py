@@ -164,7 +164,8 @@ class RawBatchFeeder(object):
         batches un-read.  Call with the lock held."""
         pending = []
         if self._staged is not None:
-            self._dev["copied"][self._staged.device_slot].synchronize()  # its copy may still be reading the pinned slot
+            if self._staged.device_slot is not None:
+                self._dev["copied"][self._staged.device_slot].synchronize()  # its copy may still be reading the pinned slot
             pending.append(self._staged)
             self._staged = None
         while True:
